@@ -1,0 +1,140 @@
+// dense_eig.cpp -- eigen-decomposition of the small projected matrix T (ncv x ncv, ncv <= a few
+// hundred) on the host, as the north star prescribes ("solves the small tridiagonal eigenproblem on
+// the host").  After a thick restart T is an arrowhead block plus a tridiagonal tail, so the general
+// symmetric path is used: Householder reduction to tridiagonal form, then implicit-shift QL with
+// accumulated transformations.  No LAPACK/Eigen exists in the image; this is self-contained.
+#include "internal.h"
+#include <algorithm>
+#include <cmath>
+#include <numeric>
+#include <vector>
+
+namespace eigkl {
+
+namespace {
+
+// a: n x n row-major symmetric.  On exit a holds the orthogonal Q with Q^T A Q = tridiag(d, e),
+// e[i] couples i-1 and i (e[0] = 0).
+void householder_tridiagonalize(int n, std::vector<double> &a, std::vector<double> &d, std::vector<double> &e) {
+  auto A = [&](int i, int j) -> double & { return a[(size_t)i * n + j]; };
+  d.assign(n, 0.0);
+  e.assign(n, 0.0);
+  for (int i = n - 1; i >= 1; --i) {
+    const int l = i - 1;
+    double h = 0.0, scale = 0.0;
+    if (l > 0) {
+      for (int k = 0; k <= l; ++k) scale += std::fabs(A(i, k));
+      if (scale == 0.0) {
+        e[i] = A(i, l);
+      } else {
+        for (int k = 0; k <= l; ++k) { A(i, k) /= scale; h += A(i, k) * A(i, k); }
+        double f = A(i, l);
+        double g = f >= 0.0 ? -std::sqrt(h) : std::sqrt(h);
+        e[i] = scale * g;
+        h -= f * g;
+        A(i, l) = f - g;
+        f = 0.0;
+        for (int j = 0; j <= l; ++j) {
+          A(j, i) = A(i, j) / h;
+          g = 0.0;
+          for (int k = 0; k <= j; ++k) g += A(j, k) * A(i, k);
+          for (int k = j + 1; k <= l; ++k) g += A(k, j) * A(i, k);
+          e[j] = g / h;
+          f += e[j] * A(i, j);
+        }
+        const double hh = f / (h + h);
+        for (int j = 0; j <= l; ++j) {
+          f = A(i, j);
+          e[j] = g = e[j] - hh * f;
+          for (int k = 0; k <= j; ++k) A(j, k) -= (f * e[k] + g * A(i, k));
+        }
+      }
+    } else {
+      e[i] = A(i, l);
+    }
+    d[i] = h;
+  }
+  d[0] = 0.0;
+  e[0] = 0.0;
+  for (int i = 0; i < n; ++i) {          // accumulate the transformation
+    const int l = i - 1;
+    if (d[i] != 0.0) {
+      for (int j = 0; j <= l; ++j) {
+        double g = 0.0;
+        for (int k = 0; k <= l; ++k) g += A(i, k) * A(k, j);
+        for (int k = 0; k <= l; ++k) A(k, j) -= g * A(k, i);
+      }
+    }
+    d[i] = A(i, i);
+    A(i, i) = 1.0;
+    for (int j = 0; j <= l; ++j) A(j, i) = A(i, j) = 0.0;
+  }
+}
+
+// implicit QL on tridiag(d, e) accumulating into z (n x n row-major, columns = eigenvectors)
+bool ql_implicit(int n, std::vector<double> &d, std::vector<double> &e, std::vector<double> &z) {
+  auto Z = [&](int i, int j) -> double & { return z[(size_t)i * n + j]; };
+  for (int i = 1; i < n; ++i) e[i - 1] = e[i];
+  e[n - 1] = 0.0;
+  for (int l = 0; l < n; ++l) {
+    int iter = 0, m;
+    do {
+      for (m = l; m < n - 1; ++m) {
+        const double dd = std::fabs(d[m]) + std::fabs(d[m + 1]);
+        if (std::fabs(e[m]) <= 2.220446049250313e-16 * dd) break;
+      }
+      if (m != l) {
+        if (iter++ == 300) return false;
+        double g = (d[l + 1] - d[l]) / (2.0 * e[l]);
+        double r = std::hypot(g, 1.0);
+        g = d[m] - d[l] + e[l] / (g + (g >= 0.0 ? std::fabs(r) : -std::fabs(r)));
+        double s = 1.0, c = 1.0, p = 0.0;
+        int i;
+        for (i = m - 1; i >= l; --i) {
+          double f = s * e[i];
+          const double b = c * e[i];
+          e[i + 1] = (r = std::hypot(f, g));
+          if (r == 0.0) {
+            d[i + 1] -= p;
+            e[m] = 0.0;
+            break;
+          }
+          s = f / r;
+          c = g / r;
+          g = d[i + 1] - p;
+          r = (d[i] - g) * s + 2.0 * c * b;
+          d[i + 1] = g + (p = s * r);
+          g = c * r - b;
+          for (int k = 0; k < n; ++k) {
+            f = Z(k, i + 1);
+            Z(k, i + 1) = s * Z(k, i) + c * f;
+            Z(k, i) = c * Z(k, i) - s * f;
+          }
+        }
+        if (r == 0.0 && i >= l) continue;
+        d[l] -= p;
+        e[l] = g;
+        e[m] = 0.0;
+      }
+    } while (m != l);
+  }
+  return true;
+}
+
+}  // namespace
+
+// a (n x n row-major, symmetric) -> eigenvectors in the columns of a, eigenvalues ascending in evals
+void sym_eig(int n, double *a_io, double *evals) {
+  std::vector<double> a(a_io, a_io + (size_t)n * n), d, e;
+  householder_tridiagonalize(n, a, d, e);
+  if (!ql_implicit(n, d, e, a)) throw Error(EIGKL_E_NOCONV, "dense eigen-solver: QL did not converge");
+  std::vector<int> idx(n);
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&](int x, int y) { return d[x] < d[y]; });
+  for (int j = 0; j < n; ++j) {
+    evals[j] = d[idx[j]];
+    for (int i = 0; i < n; ++i) a_io[(size_t)i * n + j] = a[(size_t)i * n + idx[j]];
+  }
+}
+
+}  // namespace eigkl

@@ -1,0 +1,274 @@
+// internal.h -- shared declarations of libeigkl.so (host side).  Not part of the ABI.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include "eigkl.h"
+
+namespace eigkl {
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string &m) : std::runtime_error(m), code(c) {}
+};
+
+#define EIGKL_CUDA(call)                                                                         \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      throw ::eigkl::Error(EIGKL_E_CUDA, std::string("CUDA error in ") + __FILE__ + ":" +        \
+                                             std::to_string(__LINE__) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+#define EIGKL_REQUIRE(cond, code, msg)                                                           \
+  do {                                                                                           \
+    if (!(cond)) throw ::eigkl::Error((code), (msg));                                            \
+  } while (0)
+
+// device buffer owned by the handle (plain cudaMalloc; sizes here are a few GB at most of 180 GB)
+template <typename T>
+struct DBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  DBuf() = default;
+  DBuf(const DBuf &) = delete;
+  DBuf &operator=(const DBuf &) = delete;
+  DBuf(DBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+  DBuf &operator=(DBuf &&o) noexcept {
+    if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+    return *this;
+  }
+  ~DBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr; n = 0;
+  }
+  void alloc(size_t count) {
+    release();
+    if (count == 0) count = 1;
+    EIGKL_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
+    n = count;
+  }
+  void ensure(size_t count) { if (count > n) alloc(count); }
+  size_t bytes() const { return n * sizeof(T); }
+};
+
+// pinned host buffer
+template <typename T>
+struct HBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  HBuf() = default;
+  HBuf(const HBuf &) = delete;
+  HBuf &operator=(const HBuf &) = delete;
+  ~HBuf() { if (p) cudaFreeHost(p); }
+  void ensure(size_t count) {
+    if (count <= n) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    EIGKL_CUDA(cudaMallocHost((void **)&p, count * sizeof(T)));
+    n = count;
+  }
+};
+
+struct StageTimer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  void init() {
+    EIGKL_CUDA(cudaEventCreate(&a));
+    EIGKL_CUDA(cudaEventCreate(&b));
+  }
+  void destroy() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+    a = b = nullptr;
+  }
+  void start(cudaStream_t s) { EIGKL_CUDA(cudaEventRecord(a, s)); }
+  void stop(cudaStream_t s) { EIGKL_CUDA(cudaEventRecord(b, s)); }
+  double ms() {
+    float t = 0.f;
+    EIGKL_CUDA(cudaEventSynchronize(b));
+    EIGKL_CUDA(cudaEventElapsedTime(&t, a, b));
+    return (double)t;
+  }
+};
+
+// per kernel-class profiler (EIGKL_F_PROFILE): a pool of event pairs, resolved lazily
+struct KernelProfiler {
+  bool on = false;
+  std::vector<cudaEvent_t> ev;   // pairs
+  std::vector<int> cls;
+  size_t used = 0;
+  double ms[8] = {0};
+  int64_t cnt[8] = {0};
+  void begin(int c, cudaStream_t s);
+  void end(cudaStream_t s);
+  void resolve();
+  void reset();
+  ~KernelProfiler();
+};
+enum { KC_SPMV = 0, KC_MULTIDOT = 1, KC_UPDATE = 2, KC_RESTART = 3, KC_DVALUES = 4 };
+
+// ---------------------------------------------------------------------------------------------------
+// device-resident problem state
+// ---------------------------------------------------------------------------------------------------
+struct Hypergraph {            // input pins (device) + sizes
+  int32_t n_nodes = 0, n_nets = 0;
+  int64_t n_pins = 0, n_pairs = 0;
+  DBuf<int64_t> net_off;       // n_nets+1
+  DBuf<int32_t> pins;          // n_pins
+  DBuf<int64_t> pair_off;      // n_nets+1 : exclusive scan of k(k-1)/2
+  bool loaded = false;
+};
+
+struct UniqueEdges {           // result of sort + segmented reduce: unique pairs a<b, sorted by (a,b)
+  int64_t U = 0;
+  DBuf<int32_t> a, b;
+  DBuf<float> wA;              // sum of 1.0f/(k-1) in file order (fp32)           cKL.cpp:117,128
+  DBuf<double> wL;             // sum of 2.0/k (fp64)                              cEIG.cpp:110
+  DBuf<uint32_t> first;        // pair index of the first occurrence (file order)
+  DBuf<int32_t> fstart;        // n+1 : first edge with a == v
+  DBuf<uint32_t> perm_b;       // U : edge ids sorted by (b, a)
+  DBuf<int32_t> bstart;        // n+1 : first position in perm_b with b == v
+  bool valid = false;
+};
+
+struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, diagonal included
+  int32_t n = 0;
+  int64_t nnz = 0;
+  DBuf<int32_t> rowptr, col;
+  DBuf<double> val;
+  // row blocks of the adaptive SpMV: block b owns rows [blk_row[b], blk_row[b+1])
+  int32_t n_blocks = 0;
+  DBuf<int32_t> blk_row;
+  bool valid = false;
+};
+
+struct KlCsr {                 // fp32, symmetric, rows in reference traversal order
+  int32_t n = 0;
+  int64_t nnz = 0;
+  DBuf<int32_t> rowptr, fwd_end, col;
+  DBuf<float> w;
+  int32_t n_blocks = 0;        // row blocks of the staged D-value kernel
+  DBuf<int32_t> blk_row;
+  bool valid = false;
+};
+
+struct KlState {
+  DBuf<uint8_t> state;         // bit0 = side, bit1 = locked
+  DBuf<uint32_t> rank;         // position in remain[side] (ties -> lowest rank)
+  DBuf<float> val;             // connections(v)
+  DBuf<unsigned long long> tile_key;   // 2 * n_tiles
+  DBuf<uint32_t> tile_stamp;
+  DBuf<int32_t> order0, order1;        // remain[0], remain[1]
+  int64_t n0 = 0, n1 = 0;
+  bool ascending = true;       // remain orders are ascending ids (the -EIG branch)
+  bool have_partition = false;
+  // trace on device
+  DBuf<float> t_cut, t_gain;
+  DBuf<int32_t> t_n1, t_n2;
+  DBuf<int64_t> ctrl;          // [0] swaps, [1] status
+  int64_t swaps = 0;
+  int64_t cap = 0;
+};
+
+struct EigState {
+  int32_t n = 0, ncv = 0;
+  size_t ld = 0;               // leading dimension of the basis (n rounded up)
+  DBuf<double> V[2];           // two banks of ld*(ncv+1)
+  int bank = 0;
+  DBuf<double> w[2];           // Lanczos work vector (double buffered)
+  DBuf<double> partial;        // multidot / norm partials
+  DBuf<double> hcoef;          // 2*(ncv+1) : h of pass 1 and 2
+  DBuf<double> alpha, beta;    // ncv each
+  DBuf<double> scal;           // [0] norm^2, [1] 1/beta, ...
+  DBuf<unsigned int> counters; // last-block-done counters
+  DBuf<double> Y;              // ncv*ncv restart coefficients (column major, ld = ncv)
+  DBuf<double> fiedler;        // n : result vector
+  DBuf<uint8_t> side;          // n : partition from the Fiedler vector
+  DBuf<unsigned long long> sortkey[2];
+  DBuf<uint32_t> sortval[2];
+  double lambda2 = 0, median = 0;
+  bool have_vector = false, have_median = false;
+};
+
+}  // namespace eigkl
+
+// the opaque handle
+struct eigkl_handle {
+  eigkl_opts opts{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  eigkl_stats stats{};
+  eigkl::StageTimer timer;
+  eigkl::KernelProfiler prof;
+  eigkl::Hypergraph hg;
+  eigkl::UniqueEdges ue;
+  eigkl::LaplacianCsr L;
+  eigkl::KlCsr A;
+  eigkl::KlState kl;
+  eigkl::EigState eig;
+  void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
+  void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
+  // scratch of the sort / scan primitives
+  eigkl::DBuf<int32_t> sort_hist;
+  eigkl::DBuf<int64_t> scan_tmp;
+  int64_t launches = 0;
+};
+
+namespace eigkl {
+
+// ---- primitives (scan_sort.cu) --------------------------------------------------------------------
+// exclusive scan of n int64 values (in -> out, may alias); returns nothing, total = out[n] if with_total
+void exclusive_scan_i64(eigkl_handle *h, const int64_t *in, int64_t *out, int64_t n);
+void exclusive_scan_i32(eigkl_handle *h, const int32_t *in, int32_t *out, int64_t n);
+// stable LSD radix sort of (key, val) pairs on bits [0, nbits) of the key.  keys/vals are double
+// buffers; returns the index (0/1) of the buffer holding the result.
+int radix_sort_kv(eigkl_handle *h, unsigned long long *keys[2], uint32_t *vals[2], int64_t n, int nbits);
+int bits_for(uint64_t max_value);
+
+// ---- assembly (assemble.cu) ------------------------------------------------------------------------
+void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t *net_off, const int32_t *pins);
+void build_unique_edges(eigkl_handle *h);       // sort + segmented reduce over net pins (shared by L and A)
+void assemble_laplacian(eigkl_handle *h);
+void assemble_kl_graph(eigkl_handle *h);
+
+// ---- EIG (spmv.cu, lanczos.cu, eig_solver.cpp) ------------------------------------------------------
+void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scale_inv /*device or null*/,
+                 double *store_scaled /*or null*/);
+void fiedler_solve(eigkl_handle *h);
+void partition_from_fiedler(eigkl_handle *h);
+void sym_eig(int n, double *a, double *evals);   // dense symmetric eigen-solver (host)
+
+// ---- KL (kl.cu) ---------------------------------------------------------------------------------------
+void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *order0, int64_t n0,
+                      const int32_t *order1, int64_t n1, bool ascending);
+void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev);   // ascending orders, built on device
+void kl_dvalues(eigkl_handle *h);                 // val[] for every node from the current sides
+float kl_cut0(eigkl_handle *h);
+void kl_run(eigkl_handle *h);
+
+// ---- text I/O (hgr_io.cpp) -----------------------------------------------------------------------------
+struct HostHgr {
+  int32_t n_nodes = 0, n_nets = 0;
+  std::vector<int64_t> net_off;
+  std::vector<int32_t> pins;
+};
+void parse_hgr(const char *path, HostHgr &out);
+void write_eig_file(const char *path, double lambda2, double median, const double *vec, int32_t n);
+void read_eig_file(const char *path, int32_t n, std::vector<uint8_t> &side);
+void write_trace_file(const char *path, const eigkl_trace *t);
+
+// ---- comm (comm.cpp) --------------------------------------------------------------------------------------
+void comm_init(eigkl_handle *h);
+void comm_destroy(eigkl_handle *h);
+void comm_unique_id(void *id128);
+
+inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+}  // namespace eigkl

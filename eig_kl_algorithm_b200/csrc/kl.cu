@@ -1,0 +1,590 @@
+// kl.cu -- the Kernighan-Lin pass on the GPU (north-star subsystem 3), bit-exact with cKL.cpp.
+//
+// Reference being replaced: KL(), cKL.cpp:288-390 with connections() 225-251, calCutSize() 199-223,
+// the pair selection 337-360, swip() 274-286 and updateAffectedNodeGains() 253-272; and the
+// reference's own GPU attempt, connectionsKernel + 6 host<->device crossings per swap (gKL.cu:104-145,
+// 188-227, 417-549).
+//
+// Design (B200-first):
+//  * D-value gain kernel (kl_dvalues): CSR rows in the reference's traversal order, cut into row blocks
+//    of ~2048 entries; a CTA streams col/w coalesced, gathers the neighbour's side byte, stages the
+//    SIGNED weight (+w external, -w internal) in shared memory, then one thread per row adds its
+//    entries strictly in order into two fp32 accumulators (E, I) -- the order and the two-accumulator
+//    shape are what make the result bit-identical to cKL.cpp:225-251.
+//  * The whole swap loop is ONE persistent kernel on one thread-block cluster (1..16 CTAs x 1024
+//    threads) -- KL is latency bound, so cluster barriers (~0.2 us) replace the
+//    reference's per-swap memcpys and a grid-wide sync.  Per swap:
+//      S1  argmax pair: max over per-tile cached keys (tile = 256 nodes);
+//          key = orderable(D) : ~position, so the max is the first maximum in remain[] order
+//      S2  gain = (D1 - D2) - 2 w(a,b); cut -= gain; trace row; termination counter
+//      S3  lock a, b, flip sides; every neighbour of a or b gets its D recomputed FROM SCRATCH by a
+//          warp (32 entries at a time, coalesced load + side gather, then the ordered two-accumulator
+//          sum replayed through warp shuffles)
+//      S4  tiles that contain a touched node are rescanned (first warp to stamp the tile does it)
+//    Nothing returns to the host until the pass ends; the trace is buffered in HBM.
+//  * Initial cut (kl_cut0): the reference's one-thread evaluation order, including the iteration order
+//    of its unordered_set of right nodes, rebuilt with sorts (stl_order.h explains the rule).
+#include "internal.h"
+#include "device_utils.cuh"
+#include "stl_order.h"
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <cmath>
+
+namespace cg = cooperative_groups;
+
+namespace eigkl {
+
+constexpr int KL_TILE = 256;            // nodes per argmax tile
+constexpr int KLD_THREADS = 256;
+constexpr int KLD_STAGE = 4096;         // staged signed weights per CTA (16 KB)
+constexpr int KL_LOOP_THREADS = 1024;
+constexpr int KL_MAX_CLUSTER = 16;
+constexpr int TPB = 256;
+static inline unsigned grid_for(int64_t n, int tpb = TPB) { return (unsigned)std::max<int64_t>(1, (n + tpb - 1) / tpb); }
+
+#define ST_SIDE 1u
+#define ST_LOCK 2u
+
+// ---------------------------------------------------------------------------------------------------
+// ordered two-accumulator sum of one row by a warp                       cKL.cpp:225-251
+//   E = sum of w to neighbours NOT in the left side, I = sum of w to neighbours in the left side,
+//   each added strictly in row order; returns E - I (all lanes).
+//   ov_a / ov_b: nodes whose side is taken as 1 / 0 regardless of state[] (the pair being swapped).
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_row_value(const int32_t *__restrict__ col, const float *__restrict__ w,
+                                                const uint8_t *state, int32_t lo, int32_t hi, int32_t ov_a,
+                                                int32_t ov_b, int lane) {
+  float E = 0.0f, I = 0.0f;
+  int32_t i = lo + lane;
+  int32_t c = 0;
+  float ww = 0.0f;
+  if (i < hi) { c = __ldg(col + i); ww = __ldg(w + i); }
+  for (int32_t base = lo; base < hi; base += 32) {
+    const bool valid = (base + lane) < hi;
+    // prefetch the next 32 entries while this chunk is being summed
+    int32_t cn = 0;
+    float wn = 0.0f;
+    const int32_t in = base + 32 + lane;
+    if (in < hi) { cn = __ldg(col + in); wn = __ldg(w + in); }
+    float x = 0.0f;
+    if (valid) {
+      unsigned s;
+      if (c == ov_a) s = 1u;
+      else if (c == ov_b) s = 0u;
+      else s = (unsigned)__ldcg(state + c) & ST_SIDE;
+      x = s ? ww : -ww;
+    }
+    const int cnt = min(32, hi - base);
+    for (int t = 0; t < cnt; ++t) {
+      const float xt = __shfl_sync(FULL_MASK, x, t);
+      E = __fadd_rn(E, fmaxf(xt, 0.0f));
+      I = __fadd_rn(I, fmaxf(-xt, 0.0f));
+    }
+    c = cn; ww = wn;
+  }
+  return __fsub_rn(E, I);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// D-values of every node (cKL.cpp:318-321)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(KLD_THREADS)
+dvalues_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const float *__restrict__ w,
+               const uint8_t *__restrict__ state, float *__restrict__ val, const int32_t *__restrict__ blk_row) {
+  __shared__ float sv[KLD_STAGE];
+  const int tid = threadIdx.x;
+  const int32_t r0 = blk_row[blockIdx.x], r1 = blk_row[blockIdx.x + 1];
+  if (r0 >= r1) return;
+  const int32_t e0 = rowptr[r0], e1 = rowptr[r1];
+  if (e1 - e0 <= KLD_STAGE) {
+#pragma unroll 4
+    for (int32_t i = e0 + tid; i < e1; i += KLD_THREADS) {
+      const float ww = w[i];
+      sv[i - e0] = (state[col[i]] & ST_SIDE) ? ww : -ww;
+    }
+    __syncthreads();
+    for (int32_t r = r0 + tid; r < r1; r += KLD_THREADS) {
+      const int32_t lo = rowptr[r] - e0, hi = rowptr[r + 1] - e0;
+      float E = 0.0f, I = 0.0f;
+      for (int32_t i = lo; i < hi; ++i) {
+        const float x = sv[i];
+        E = __fadd_rn(E, fmaxf(x, 0.0f));
+        I = __fadd_rn(I, fmaxf(-x, 0.0f));
+      }
+      val[r] = __fsub_rn(E, I);
+    }
+  } else {                              // a row longer than the staging buffer shares this block
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int32_t r = r0 + warp; r < r1; r += KLD_THREADS / 32) {
+      const float v = warp_row_value(col, w, state, rowptr[r], rowptr[r + 1], -1, -1, lane);
+      if (lane == 0) val[r] = v;
+    }
+  }
+}
+
+void kl_dvalues(eigkl_handle *h) {
+  auto &A = h->A;
+  auto &k = h->kl;
+  EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "KL graph not assembled");
+  EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "no partition set");
+  h->prof.begin(KC_DVALUES, h->stream);
+  dvalues_kernel<<<(unsigned)A.n_blocks, KLD_THREADS, 0, h->stream>>>(A.rowptr.p, A.col.p, A.w.p, k.state.p, k.val.p, A.blk_row.p);
+  h->prof.end(h->stream);
+  h->launches++;
+  EIGKL_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------------
+// partition set-up
+// ---------------------------------------------------------------------------------------------------
+__global__ void side_flag_kernel(const uint8_t *__restrict__ side, int32_t n, int32_t *__restrict__ is0, int *__restrict__ err) {
+  int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) {
+    const uint8_t s = side[v];
+    if (s > 1) atomicOr(err, 1);
+    is0[v] = (s == 0) ? 1 : 0;
+  }
+}
+__global__ void build_orders_kernel(const uint8_t *__restrict__ side, const int32_t *__restrict__ pos0, int32_t n,
+                                    int32_t *__restrict__ order0, int32_t *__restrict__ order1, uint8_t *__restrict__ state,
+                                    uint32_t *__restrict__ rank) {
+  int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= n) return;
+  const int32_t p0 = pos0[v];
+  if (side[v] == 0) { order0[p0] = v; rank[v] = (uint32_t)p0; state[v] = 0; }
+  else              { order1[v - p0] = v; rank[v] = (uint32_t)(v - p0); state[v] = ST_SIDE; }
+}
+__global__ void apply_order_kernel(const int32_t *__restrict__ order, int64_t cnt, uint8_t s, int32_t n, uint8_t *__restrict__ state,
+                                   uint32_t *__restrict__ rank, int32_t *__restrict__ seen, int *__restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cnt) return;
+  const int32_t v = order[i];
+  if (v < 0 || v >= n) { atomicOr(err, 1); return; }
+  if (atomicAdd(&seen[v], 1) != 0) atomicOr(err, 2);
+  state[v] = s;
+  rank[v] = (uint32_t)i;
+}
+
+static void kl_alloc_state(eigkl_handle *h, int32_t n) {
+  auto &k = h->kl;
+  k.state.ensure((size_t)n); k.rank.ensure((size_t)n); k.val.ensure((size_t)n);
+  k.order0.ensure((size_t)n); k.order1.ensure((size_t)n);
+  const int64_t n_tiles = ceil_div(n, KL_TILE);
+  k.tile_key.ensure((size_t)(2 * n_tiles + 2 * KL_MAX_CLUSTER + 8));
+  k.tile_stamp.ensure((size_t)n_tiles + 1);
+  k.ctrl.ensure(8);
+}
+
+void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
+  const int32_t n = h->hg.n_nodes;
+  auto &k = h->kl;
+  kl_alloc_state(h, n);
+  DBuf<int32_t> pos; pos.alloc((size_t)n + 1);
+  DBuf<int> err; err.alloc(1);
+  EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
+  side_flag_kernel<<<grid_for(n), TPB, 0, h->stream>>>(side_dev, n, pos.p, err.p);
+  exclusive_scan_i32(h, pos.p, pos.p, n);
+  build_orders_kernel<<<grid_for(n), TPB, 0, h->stream>>>(side_dev, pos.p, n, k.order0.p, k.order1.p, k.state.p, k.rank.p);
+  h->launches += 2;
+  int32_t n0 = 0; int herr = 0;
+  EIGKL_CUDA(cudaMemcpyAsync(&n0, pos.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EIGKL_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  EIGKL_REQUIRE(herr == 0, EIGKL_E_FORMAT, "partition side not in {0,1}");
+  k.n0 = n0; k.n1 = n - n0; k.ascending = true; k.have_partition = true;
+}
+
+void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *order0, int64_t n0,
+                      const int32_t *order1, int64_t n1, bool ascending) {
+  EIGKL_REQUIRE(h->hg.loaded, EIGKL_E_ARG, "no hypergraph loaded");
+  const int32_t n = h->hg.n_nodes;
+  auto &k = h->kl;
+  if (ascending) {
+    EIGKL_REQUIRE(side_host != nullptr, EIGKL_E_ARG, "side is NULL");
+    DBuf<uint8_t> side; side.alloc((size_t)n);
+    EIGKL_CUDA(cudaMemcpyAsync(side.p, side_host, (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    kl_set_partition_device(h, side.p);
+    return;
+  }
+  EIGKL_REQUIRE(order0 && order1 && n0 >= 0 && n1 >= 0 && n0 + n1 == n, EIGKL_E_ARG, "orders must cover every node once");
+  kl_alloc_state(h, n);
+  DBuf<int32_t> seen; seen.alloc((size_t)n);
+  DBuf<int> err; err.alloc(1);
+  EIGKL_CUDA(cudaMemsetAsync(seen.p, 0, (size_t)n * sizeof(int32_t), h->stream));
+  EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
+  EIGKL_CUDA(cudaMemcpyAsync(k.order0.p, order0, (size_t)n0 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  EIGKL_CUDA(cudaMemcpyAsync(k.order1.p, order1, (size_t)n1 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+  if (n0) apply_order_kernel<<<grid_for(n0), TPB, 0, h->stream>>>(k.order0.p, n0, 0, n, k.state.p, k.rank.p, seen.p, err.p);
+  if (n1) apply_order_kernel<<<grid_for(n1), TPB, 0, h->stream>>>(k.order1.p, n1, ST_SIDE, n, k.state.p, k.rank.p, seen.p, err.p);
+  h->launches += 2;
+  int herr = 0;
+  EIGKL_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  EIGKL_REQUIRE(herr == 0, EIGKL_E_ARG, "orders must cover every node exactly once");
+  k.n0 = n0; k.n1 = n1; k.ascending = false; k.have_partition = true;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// initial cut in the reference's one-thread order                         cKL.cpp:199-223
+// ---------------------------------------------------------------------------------------------------
+__global__ void set_first_kernel(const int32_t *__restrict__ seq, int32_t L, uint32_t B, uint32_t *__restrict__ first) {
+  int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < L) atomicMin(&first[(uint32_t)seq[t] % B], (uint32_t)t);
+}
+__global__ void set_keys_kernel(const int32_t *__restrict__ seq, int32_t L, uint32_t B, const uint32_t *__restrict__ first,
+                                unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals) {
+  int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < L) {
+    // reversed sequence, stable sort by descending first-hit time of the bucket (see stl_order.h)
+    const uint32_t f = first[(uint32_t)seq[t] % B];
+    keys[L - 1 - t] = (unsigned long long)((uint32_t)(L - 1) - f);
+    vals[L - 1 - t] = (uint32_t)seq[t];
+  }
+}
+__global__ void set_rank_kernel(const uint32_t *__restrict__ ordered, int32_t L, uint32_t *__restrict__ set_rank) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < L) set_rank[ordered[i]] = (uint32_t)i;
+}
+// cut entries of the left rows: key = position of the row in remain[0] : forward/backward : order inside
+__global__ void cut_entries_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ fwd_end,
+                                   const int32_t *__restrict__ col, const uint8_t *__restrict__ state,
+                                   const uint32_t *__restrict__ rank, const uint32_t *__restrict__ set_rank, int32_t n,
+                                   int qb, unsigned long long *__restrict__ keys, uint32_t *__restrict__ vals,
+                                   unsigned int *__restrict__ count) {
+  // one warp per row
+  const int lane = threadIdx.x & 31;
+  const int32_t v = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (v >= n) return;
+  if (state[v] & ST_SIDE) return;                                   // only rows of remain[0]
+  const int32_t lo = rowptr[v], fe = fwd_end[v], hi = rowptr[v + 1];
+  const unsigned long long rowkey = (unsigned long long)rank[v] << (qb + 1);
+  for (int32_t i = lo + lane; i < hi; i += 32) {
+    const int32_t c = col[i];
+    if (!(state[c] & ST_SIDE)) continue;                            // rightNodes.count(neighbor)
+    unsigned long long key;
+    if (i < fe) key = rowkey | (unsigned long long)(uint32_t)(i - lo);                       // map order
+    else        key = rowkey | (1ull << qb) | (unsigned long long)set_rank[c];               // set order
+    const unsigned int slot = atomicAdd(count, 1u);
+    keys[slot] = key;
+    vals[slot] = (uint32_t)i;
+  }
+}
+// one warp: strictly sequential fp32 sum of w[vals[i]], i ascending
+__global__ void ordered_sum_kernel(const uint32_t *__restrict__ vals, const float *__restrict__ w, int64_t m, float *__restrict__ out) {
+  const int lane = threadIdx.x;
+  float s = 0.0f;
+  float x = (lane < m) ? w[vals[lane]] : 0.0f;
+  for (int64_t base = 0; base < m; base += 32) {
+    const int64_t in = base + 32 + lane;
+    const float xn = (in < m) ? w[vals[in]] : 0.0f;
+    const int cnt = (int)min((int64_t)32, m - base);
+    for (int t = 0; t < cnt; ++t) s = __fadd_rn(s, __shfl_sync(FULL_MASK, x, t));
+    x = xn;
+  }
+  if (lane == 0) out[0] = s;
+}
+
+float kl_cut0(eigkl_handle *h) {
+  auto &A = h->A;
+  auto &k = h->kl;
+  auto &e = h->eig;
+  EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "KL graph not assembled");
+  EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "no partition set");
+  const int32_t n = A.n;
+  const int32_t n1 = (int32_t)k.n1;
+  cudaStream_t st = h->stream;
+  const size_t need = (size_t)std::max<int64_t>(std::max<int64_t>(A.nnz, n), 16) + 1;
+  for (int i = 0; i < 2; ++i) { e.sortkey[i].ensure(need); e.sortval[i].ensure(need); }
+  unsigned long long *keys[2] = {e.sortkey[0].p, e.sortkey[1].p};
+  uint32_t *vals[2] = {e.sortval[0].p, e.sortval[1].p};
+  DBuf<uint32_t> set_rank; set_rank.alloc((size_t)n);
+  DBuf<int32_t> seq; seq.alloc((size_t)std::max(n1, 1));
+  // (1) iteration order of unordered_set<uint32_t>(remain[1].begin(), remain[1].end())
+  if (n1 > 0) {
+    const uint32_t Bfinal = stl_final_buckets((uint32_t)n1);
+    DBuf<uint32_t> first; first.alloc(Bfinal);
+    int32_t done = 0;                                   // elements already in seq
+    for (int lv = 0; lv < STL_CHAIN_LEN; ++lv) {
+      const uint32_t B = stl_bucket_chain(lv);
+      const int32_t L = (int32_t)std::min<int64_t>(n1, B);
+      // append remain[1][done .. L)
+      EIGKL_CUDA(cudaMemcpyAsync(seq.p + done, k.order1.p + done, (size_t)(L - done) * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      EIGKL_CUDA(cudaMemsetAsync(first.p, 0xFF, (size_t)B * sizeof(uint32_t), st));
+      set_first_kernel<<<grid_for(L), TPB, 0, st>>>(seq.p, L, B, first.p);
+      set_keys_kernel<<<grid_for(L), TPB, 0, st>>>(seq.p, L, B, first.p, keys[0], vals[0]);
+      h->launches += 2;
+      const int cur = radix_sort_kv(h, keys, vals, L, bits_for((uint64_t)std::max(L - 1, 1)));
+      EIGKL_CUDA(cudaMemcpyAsync(seq.p, vals[cur], (size_t)L * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+      done = L;
+      if ((int64_t)B >= n1) break;
+    }
+    set_rank_kernel<<<grid_for(n1), TPB, 0, st>>>(reinterpret_cast<const uint32_t *>(seq.p), n1, set_rank.p);
+    h->launches++;
+  }
+  // (2) cut entries keyed by evaluation order, (3) sort, (4) ordered sum
+  EIGKL_CUDA(cudaMemsetAsync(k.ctrl.p + 4, 0, sizeof(int64_t), st));
+  unsigned int *count = reinterpret_cast<unsigned int *>(k.ctrl.p + 4);
+  const int qb = bits_for((uint64_t)std::max(n - 1, 1));
+  cut_entries_kernel<<<grid_for((int64_t)n * 32), TPB, 0, st>>>(A.rowptr.p, A.fwd_end.p, A.col.p, k.state.p, k.rank.p, set_rank.p, n, qb,
+                                                              keys[0], vals[0], count);
+  h->launches++;
+  unsigned int m = 0;
+  EIGKL_CUDA(cudaMemcpyAsync(&m, count, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+  EIGKL_CUDA(cudaStreamSynchronize(st));
+  const int kb = bits_for((uint64_t)std::max<int64_t>(k.n0 - 1, 1)) + 1 + qb;
+  const int cur = radix_sort_kv(h, keys, vals, m, kb);
+  float *out = reinterpret_cast<float *>(k.ctrl.p + 5);
+  ordered_sum_kernel<<<1, 32, 0, st>>>(vals[cur], A.w.p, (int64_t)m, out);
+  h->launches++;
+  float cut = 0.0f;
+  EIGKL_CUDA(cudaMemcpyAsync(&cut, out, sizeof(float), cudaMemcpyDeviceToHost, st));
+  EIGKL_CUDA(cudaStreamSynchronize(st));
+  EIGKL_CUDA(cudaGetLastError());
+  return cut;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// tile keys
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tile_scan(const uint8_t *state, const float *val, const uint32_t *__restrict__ rank, int32_t n,
+                                          int32_t tile, int lane, unsigned long long &k0, unsigned long long &k1) {
+  k0 = 0ull; k1 = 0ull;
+  const int32_t base = tile * KL_TILE;
+#pragma unroll
+  for (int r = 0; r < KL_TILE / 32; ++r) {
+    const int32_t u = base + r * 32 + lane;
+    if (u < n) {
+      const unsigned s = __ldcg(state + u);
+      if (!(s & ST_LOCK)) {
+        const float v = __ldcg(val + u);
+        const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - __ldg(rank + u));
+        if (s & ST_SIDE) { const unsigned long long key = ((unsigned long long)float_orderable(-v) << 32) | low; k1 = key > k1 ? key : k1; }
+        else             { const unsigned long long key = ((unsigned long long)float_orderable(v) << 32) | low;  k0 = key > k0 ? key : k0; }
+      }
+    }
+  }
+  k0 = warp_max_u64(k0);
+  k1 = warp_max_u64(k1);
+}
+__global__ void tile_init_kernel(const uint8_t *__restrict__ state, const float *__restrict__ val, const uint32_t *__restrict__ rank,
+                                 int32_t n, int32_t n_tiles, unsigned long long *__restrict__ tile_key, uint32_t *__restrict__ tile_stamp) {
+  const int lane = threadIdx.x & 31;
+  const int32_t tile = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+  if (tile >= n_tiles) return;
+  unsigned long long k0, k1;
+  tile_scan(state, val, rank, n, tile, lane, k0, k1);
+  if (lane == 0) { tile_key[2 * tile] = k0; tile_key[2 * tile + 1] = k1; tile_stamp[tile] = 0u; }
+}
+
+__device__ __forceinline__ float float_from_orderable(uint32_t u) {
+  u = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u;
+  return __uint_as_float(u);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// the persistent swap loop
+// ---------------------------------------------------------------------------------------------------
+struct KlLoopParams {
+  int32_t n, n_tiles;
+  const int32_t *rowptr, *col;
+  const float *w;
+  uint8_t *state;
+  const uint32_t *rank;
+  float *val;
+  unsigned long long *tile_key;     // 2*n_tiles, then the exchange area 2*KL_MAX_CLUSTER
+  uint32_t *tile_stamp;
+  const int32_t *order0, *order1;
+  float *t_cut, *t_gain;
+  int32_t *t_n1, *t_n2;
+  int64_t *ctrl;
+  float cut0;
+  uint32_t term_limit;
+  int64_t n0, n1;
+};
+
+__global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoopParams p) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned nc = cluster.num_blocks();
+  const unsigned cr = cluster.block_rank();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned gwarp = cr * (KL_LOOP_THREADS / 32) + warp;
+  const unsigned total_warps = nc * (KL_LOOP_THREADS / 32);
+  const unsigned gtid = cr * KL_LOOP_THREADS + tid;
+  const unsigned total_threads = nc * KL_LOOP_THREADS;
+  unsigned long long *exch = p.tile_key + 2 * (size_t)p.n_tiles;
+
+  __shared__ unsigned long long red0[32], red1[32];
+  __shared__ unsigned long long sh_best[2];
+  __shared__ float sh_w;
+  __shared__ float sh_cut;
+  __shared__ uint32_t sh_term, sh_iter;
+  __shared__ int sh_done;
+  __shared__ long long sh_rem0, sh_rem1;
+  if (tid == 0) {
+    sh_cut = p.cut0; sh_term = 0; sh_iter = 0; sh_done = 0; sh_rem0 = p.n0; sh_rem1 = p.n1;
+    if (p.n0 <= 0 || p.n1 <= 0) sh_done = 1;
+  }
+  __syncthreads();
+
+  while (!sh_done) {
+    // ---- S1: best pair over the cached tile keys ------------------------------------------------
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    for (uint32_t t = gtid; t < (uint32_t)p.n_tiles; t += total_threads) {
+      const unsigned long long a0 = __ldcg(p.tile_key + 2 * (size_t)t), a1 = __ldcg(p.tile_key + 2 * (size_t)t + 1);
+      k0 = a0 > k0 ? a0 : k0;
+      k1 = a1 > k1 ? a1 : k1;
+    }
+    k0 = warp_max_u64(k0);
+    k1 = warp_max_u64(k1);
+    if (lane == 0) { red0[warp] = k0; red1[warp] = k1; }
+    __syncthreads();
+    if (warp == 0) {
+      k0 = warp_max_u64(red0[lane]);
+      k1 = warp_max_u64(red1[lane]);
+      if (lane == 0) {
+        if (nc > 1) { __stcg(exch + 2 * cr, k0); __stcg(exch + 2 * cr + 1, k1); }
+        else { sh_best[0] = k0; sh_best[1] = k1; }
+      }
+    }
+    if (nc > 1) {
+      cluster.sync();
+      if (warp == 0) {
+        k0 = lane < (int)nc ? __ldcg(exch + 2 * lane) : 0ull;
+        k1 = lane < (int)nc ? __ldcg(exch + 2 * lane + 1) : 0ull;
+        k0 = warp_max_u64(k0);
+        k1 = warp_max_u64(k1);
+        if (lane == 0) { sh_best[0] = k0; sh_best[1] = k1; }
+      }
+    }
+    if (tid == 0) sh_w = 0.0f;
+    __syncthreads();
+    const unsigned long long b0 = sh_best[0], b1 = sh_best[1];
+    if (b0 == 0ull || b1 == 0ull) {                  // no selectable node on one side (cKL.cpp:387-389)
+      if (tid == 0) sh_done = 1;
+      __syncthreads();
+      break;
+    }
+    const int32_t a = __ldg(p.order0 + (0xFFFFFFFFu - (uint32_t)(b0 & 0xFFFFFFFFull)));
+    const int32_t b = __ldg(p.order1 + (0xFFFFFFFFu - (uint32_t)(b1 & 0xFFFFFFFFull)));
+    const int32_t alo = __ldg(p.rowptr + a), ahi = __ldg(p.rowptr + a + 1);
+    const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
+    // ---- S2: gain, cut, trace, termination (every CTA computes the same values) --------------------
+    for (int32_t i = alo + tid; i < ahi; i += KL_LOOP_THREADS)
+      if (__ldg(p.col + i) == b) sh_w = __ldg(p.w + i);              // getEdgeWeight, cKL.cpp:75-82
+    __syncthreads();
+    if (tid == 0) {
+      const float maxGain = float_from_orderable((uint32_t)(b0 >> 32));
+      const float minGain = __fsub_rn(0.0f, float_from_orderable((uint32_t)(b1 >> 32)));
+      const float gain = __fsub_rn(__fsub_rn(maxGain, minGain), __fmul_rn(2.0f, sh_w));   // cKL.cpp:360
+      const float cut = __fsub_rn(sh_cut, gain);                                          // cKL.cpp:362
+      sh_cut = cut;
+      const uint32_t it = ++sh_iter;
+      if (cr == 0) {
+        p.t_cut[it] = cut; p.t_gain[it] = gain; p.t_n1[it] = a; p.t_n2[it] = b;
+        __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));          // swip, cKL.cpp:274-286
+        __stcg(p.state + b, (uint8_t)(ST_LOCK));
+      }
+      if (gain <= 0.0f) { if (++sh_term > p.term_limit) sh_done = 1; }   // cKL.cpp:382-386
+      else sh_term = 0;
+      if (--sh_rem0 == 0) sh_done = 1;
+      if (--sh_rem1 == 0) sh_done = 1;
+    }
+    // ---- S3: recompute D of every neighbour of a or b from scratch (cKL.cpp:253-272) -----------------
+    const int32_t da = ahi - alo, items = da + (bhi - blo);
+    for (int32_t it = gwarp; it < items; it += total_warps) {
+      const int32_t v = __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
+      const float nv = warp_row_value(p.col, p.w, p.state, __ldg(p.rowptr + v), __ldg(p.rowptr + v + 1), a, b, lane);
+      if (lane == 0) __stcg(p.val + v, nv);
+    }
+    cluster.sync();
+    // ---- S4: rescan the tiles that contain a touched node -----------------------------------------
+    const uint32_t stamp = sh_iter;
+    for (int32_t it = gwarp; it < items + 2; it += total_warps) {
+      int32_t v;
+      if (it < da) v = __ldg(p.col + alo + it);
+      else if (it < items) v = __ldg(p.col + blo + (it - da));
+      else v = (it == items) ? a : b;
+      const int32_t tile = v / KL_TILE;
+      unsigned claimed = 0;
+      if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
+      claimed = __shfl_sync(FULL_MASK, claimed, 0);
+      if (claimed) {
+        unsigned long long t0, t1;
+        tile_scan(p.state, p.val, p.rank, p.n, tile, lane, t0, t1);
+        if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
+      }
+    }
+    cluster.sync();
+  }
+  if (cr == 0 && tid == 0) { p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1; }
+}
+
+void kl_run(eigkl_handle *h) {
+  auto &A = h->A;
+  auto &k = h->kl;
+  EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "eigkl_kl_run: call eigkl_assemble_kl_graph first");
+  EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "eigkl_kl_run: no initial partition");
+  const int32_t n = A.n;
+  cudaStream_t st = h->stream;
+  const int64_t cap = std::min(k.n0, k.n1) + 1;
+  k.t_cut.ensure((size_t)cap); k.t_gain.ensure((size_t)cap); k.t_n1.ensure((size_t)cap); k.t_n2.ensure((size_t)cap);
+  k.cap = cap;
+  // set-up: initial cut (row 0), D-values of every node, tile keys
+  h->timer.start(st);
+  const float cut0 = kl_cut0(h);                                     // cKL.cpp:306
+  kl_dvalues(h);                                                     // cKL.cpp:318-321
+  const int32_t n_tiles = (int32_t)ceil_div(n, KL_TILE);
+  tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, n, n_tiles, k.tile_key.p, k.tile_stamp.p);
+  h->launches++;
+  const float zero = 0.0f; const int32_t neg = -1;
+  EIGKL_CUDA(cudaMemcpyAsync(k.t_cut.p, &cut0, sizeof(float), cudaMemcpyHostToDevice, st));
+  EIGKL_CUDA(cudaMemcpyAsync(k.t_gain.p, &zero, sizeof(float), cudaMemcpyHostToDevice, st));
+  EIGKL_CUDA(cudaMemcpyAsync(k.t_n1.p, &neg, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  EIGKL_CUDA(cudaMemcpyAsync(k.t_n2.p, &neg, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  EIGKL_CUDA(cudaMemsetAsync(k.ctrl.p, 0, 2 * sizeof(int64_t), st));
+  h->timer.stop(st);
+  h->stats.ms_kl_setup = h->timer.ms();
+
+  KlLoopParams p;
+  p.n = n; p.n_tiles = n_tiles;
+  p.rowptr = A.rowptr.p; p.col = A.col.p; p.w = A.w.p;
+  p.state = k.state.p; p.rank = k.rank.p; p.val = k.val.p;
+  p.tile_key = k.tile_key.p; p.tile_stamp = k.tile_stamp.p;
+  p.order0 = k.order0.p; p.order1 = k.order1.p;
+  p.t_cut = k.t_cut.p; p.t_gain = k.t_gain.p; p.t_n1 = k.t_n1.p; p.t_n2 = k.t_n2.p;
+  p.ctrl = k.ctrl.p;
+  p.cut0 = cut0;
+  p.term_limit = (uint32_t)std::log2((double)n) + 5;                 // cKL.cpp:303
+  p.n0 = k.n0; p.n1 = k.n1;
+
+  int nc = h->opts.kl_cluster;
+  if (nc <= 0) nc = (n <= 4096) ? 1 : 8;
+  EIGKL_REQUIRE(nc == 1 || nc == 2 || nc == 4 || nc == 8 || nc == 16, EIGKL_E_ARG, "kl_cluster must be 1, 2, 4, 8 or 16");
+  if (nc > 8) EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)nc);
+  cfg.blockDim = dim3(KL_LOOP_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  h->timer.start(st);
+  EIGKL_CUDA(cudaLaunchKernelEx(&cfg, kl_loop_kernel, p));
+  h->launches++;
+  h->timer.stop(st);
+  int64_t ctrl[2] = {0, 0};
+  EIGKL_CUDA(cudaMemcpyAsync(ctrl, k.ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
+  EIGKL_CUDA(cudaStreamSynchronize(st));
+  EIGKL_CUDA(cudaGetLastError());
+  h->stats.ms_kl_loop = h->timer.ms();
+  EIGKL_REQUIRE(ctrl[1] == 1, EIGKL_E_CUDA, "KL kernel did not complete");
+  k.swaps = ctrl[0];
+  h->stats.kl_swaps = k.swaps;
+  h->stats.kl_cluster = nc;
+  h->stats.kl_threads = nc * KL_LOOP_THREADS;
+}
+
+}  // namespace eigkl

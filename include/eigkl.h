@@ -1,0 +1,174 @@
+/*
+ * eigkl.h -- C ABI of libeigkl.so, the B200-native (sm_100a) EIG+KL bipartitioner.
+ *
+ * This is the drop-in boundary for the hot path of yhinai/EIG-KL-Algorithm.  The reference has no
+ * library or FFI surface: its operator surface is three executables coupled by text files
+ * (SURVEY.md section 8b).  Each entry point below therefore names the reference code it replaces;
+ * the executables cEIG / cKL / gKL shipped with this repo (eig_kl_algorithm_b200/cli/) are ~60-line
+ * callers of this ABI that keep the reference's argv, file names, formats and exit codes.
+ *
+ * Conventions: plain C types only; every function returns an int status (EIGKL_OK == 0, negative
+ * on error) and never throws; eigkl_last_error() gives the message.  The caller owns every host
+ * buffer it passes; the handle owns all device memory, one CUDA stream and (optionally) one NCCL
+ * communicator.  A handle is not thread-safe; use one handle per GPU / rank.
+ * There is no CPU fallback: every compute entry point fails with EIGKL_E_CUDA without a GPU.
+ */
+#ifndef EIGKL_H
+#define EIGKL_H
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EIGKL_ABI_VERSION 1
+
+enum {
+  EIGKL_OK        = 0,
+  EIGKL_E_ARG     = -1,   /* bad argument / call order                               */
+  EIGKL_E_IO      = -2,   /* cannot open / read / write a file                       */
+  EIGKL_E_FORMAT  = -3,   /* malformed .hgr or EIG file, pin id out of range, duplicate pin in a net */
+  EIGKL_E_CUDA    = -4,   /* CUDA runtime error or no usable device                  */
+  EIGKL_E_NCCL    = -5,   /* NCCL error                                              */
+  EIGKL_E_NOCONV  = -6,   /* Lanczos did not converge within max_restarts            */
+  EIGKL_E_NOMEM   = -7
+};
+
+typedef struct eigkl_handle eigkl_handle;
+
+/* options; zero-initialise and override.  sizeof is checked through struct_size. */
+typedef struct {
+  uint32_t struct_size;      /* = sizeof(eigkl_opts)                                              */
+  int32_t  device;           /* CUDA device ordinal (default 0)                                   */
+  int32_t  rank, nranks;     /* row-partition rank / world size (default 0 / 1)                   */
+  const void *nccl_unique_id;/* 128-byte ncclUniqueId shared by all ranks, or NULL when nranks==1 */
+  /* Fiedler solve -- defaults restate cEIG.cpp:195-198 (Spectra: nev=2, ncv=min(100,n/2),
+   * tol=1e-10, maxit=1000)                                                                        */
+  int32_t  ncv;              /* 0 => min(100, n/2)                                                */
+  int32_t  max_restarts;     /* 0 => 1000                                                         */
+  double   tol;              /* 0 => 1e-10                                                        */
+  int32_t  keep;             /* Ritz vectors kept at a thick restart; 0 => library default        */
+  uint64_t seed;             /* start-vector seed (the reference's is Spectra's fixed seed 0)     */
+  /* KL */
+  int32_t  kl_cluster;       /* CTAs in the KL cluster (1,2,4,8,16); 0 => chosen from the size    */
+  uint32_t flags;            /* EIGKL_F_*                                                         */
+} eigkl_opts;
+
+#define EIGKL_F_PROFILE   0x1u  /* bracket every kernel class with CUDA events (see eigkl_stats)  */
+#define EIGKL_F_NO_GRAPH  0x2u  /* launch Lanczos steps directly instead of replaying a CUDA graph */
+
+/* per-call statistics.  Times are device times from CUDA events on the handle's stream, in ms.   */
+typedef struct {
+  uint32_t struct_size;
+  /* sizes */
+  int64_t  n_nodes, n_nets, n_pins, n_pairs;  /* pairs = sum k(k-1)/2                              */
+  int64_t  nnz_laplacian;                     /* symmetric off-diagonals + diagonals               */
+  int64_t  nnz_kl;                            /* symmetric off-diagonals of the KL graph           */
+  /* Fiedler solve */
+  int32_t  ncv, matvecs, restarts, converged;
+  double   resid_est[2];                      /* |beta_m * y_last| of the two wanted Ritz pairs    */
+  double   lambda[2];                         /* the two smallest Ritz values (ascending)          */
+  /* KL */
+  int64_t  kl_swaps;
+  int32_t  kl_cluster, kl_threads;
+  /* kernel launches issued by this handle since creation (graph replays count their nodes)        */
+  int64_t  gpu_launches;
+  /* device time per stage of the last call of each kind (always measured, 2 events per stage)     */
+  double   ms_assemble_laplacian, ms_assemble_kl, ms_fiedler, ms_partition, ms_kl_setup, ms_kl_loop;
+  /* per kernel class, only with EIGKL_F_PROFILE: summed device time and launch count              */
+  double   ms_spmv, ms_multidot, ms_update, ms_restart, ms_dvalues;
+  int64_t  n_spmv, n_multidot, n_update, n_restart, n_dvalues;
+  /* algorithmic bytes of ONE launch of the kernel class at this problem size          */
+  double   bytes_spmv, bytes_dvalues;
+  double   bytes_multidot_total, bytes_update_total;   /* summed over the profiled launches        */
+} eigkl_stats;
+
+/* KL trace, one row per swap plus row 0 (the initial cut) -- the rows cKL writes to
+ * results/<base>_KL_CutSize[_EIG]_output.txt (cKL.cpp:315,380) plus the swapped node ids.
+ * Arrays are caller-owned with `capacity` entries (need min(|left|,|right|)+1); any may be NULL.  */
+typedef struct {
+  int64_t  capacity;
+  int64_t  swaps;            /* out: rows 1..swaps are swaps                                      */
+  float   *cut;              /* cut[0] = initial cut; cut[i] = cut after swap i                   */
+  float   *gain;             /* gain[0] = 0                                                       */
+  int32_t *node1, *node2;    /* node1 leaves side 0, node2 leaves side 1 (0-based); -1 in row 0   */
+} eigkl_trace;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int  eigkl_abi_version(void);
+/* fills id[128] with a fresh ncclUniqueId (rank 0 calls it, then shares it with the other ranks) */
+int  eigkl_nccl_unique_id(void *id128);
+int  eigkl_create(eigkl_handle **out, const eigkl_opts *opts);
+void eigkl_destroy(eigkl_handle *h);
+const char *eigkl_last_error(const eigkl_handle *h);   /* h may be NULL: error of a failed create */
+int  eigkl_get_stats(const eigkl_handle *h, eigkl_stats *out);
+int  eigkl_synchronize(eigkl_handle *h);
+
+/* ---- input: the hypergraph ------------------------------------------------------------------- */
+/* Parses a .hgr file: header "<nets> <nodes>", then <nets> lines of 1-based pin ids.
+ * Replaces cEIG.cpp:178-182,94-101 ; cKL.cpp:92-115 ; gKL.cu:581-620.                            */
+int  eigkl_load_hgr(eigkl_handle *h, const char *path);
+/* Same, from host arrays: net e has pins[net_off[e] .. net_off[e+1]) (0-based node ids).         */
+int  eigkl_set_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets,
+                    const int64_t *net_off, const int32_t *pins);
+int  eigkl_get_sizes(const eigkl_handle *h, int32_t *n_nodes, int32_t *n_nets, int64_t *n_pins);
+
+/* ---- EIG stage (the cEIG executable) ---------------------------------------------------------- */
+/* Clique-model Laplacian L = D - A, A_ij = sum over nets containing i and j of 2.0/|net| (fp64), as a
+ * GPU sort + segmented reduce over net pins.  Replaces initializeMatrix, cEIG.cpp:86-133.        */
+int  eigkl_assemble_laplacian(eigkl_handle *h);
+/* Two algebraically smallest eigenpairs of L by restarted Lanczos; reports the larger one
+ * (lambda2, Fiedler vector, unit norm).  Replaces the Spectra call cEIG.cpp:194-207.
+ * lambda2 / vec (n_nodes doubles, host) may be NULL: the vector then stays on the device.        */
+int  eigkl_fiedler(eigkl_handle *h, double *lambda2, double *vec);
+/* median of the Fiedler vector (cEIG.cpp:55-65) and side_i = (median > v_i) (cEIG.cpp:218), on the
+ * device; makes that partition the KL initial partition (the fused pipeline gKL2.cu:1018-1024
+ * aimed at).  median / side (n_nodes bytes, host) may be NULL.                                   */
+int  eigkl_partition_from_fiedler(eigkl_handle *h, double *median, uint8_t *side);
+/* Writes pre_saved_EIG/<base>_out.txt: lambda2, median, then "i\tside\tv_i" with 12 significant
+ * digits.  Replaces cEIG.cpp:213-220.                                                            */
+int  eigkl_write_eig(eigkl_handle *h, const char *path);
+
+/* ---- KL stage (the cKL / gKL executables) ------------------------------------------------------ */
+/* KL graph: A[a][b] += 1.0f/(|net|-1) in file order (fp32), rows stored in the reference's traversal
+ * order (forward neighbours in libstdc++ unordered_map order, then backward neighbours ascending).
+ * Replaces InitializeSparsMatrix + initNodeConnections, cKL.cpp:84-149,53-72 ; gKL.cu:573-666.   */
+int  eigkl_assemble_kl_graph(eigkl_handle *h);
+/* Initial partition.  side[i] in {0,1}; remain[0]/remain[1] are the nodes of each side in ascending
+ * id order (what the -EIG branch produces).  Replaces shuffleSparceMatrix, cKL.cpp:151-174.      */
+int  eigkl_set_partition(eigkl_handle *h, const uint8_t *side);
+/* Same with explicit remain[] orders (the random branch, cKL.cpp:175-193, with the shuffle done by
+ * the caller): ties in the pair selection go to the earlier position.                            */
+int  eigkl_set_partition_ordered(eigkl_handle *h, const int32_t *order0, int64_t n0,
+                                 const int32_t *order1, int64_t n1);
+/* Reads the side column of a pre_saved_EIG file the way cKL does (skip 2 lines, "node side w").
+ * Replaces cKL.cpp:155-174 ; gKL.cu:270-300.                                                     */
+int  eigkl_load_eig(eigkl_handle *h, const char *path);
+/* One KL pass: D-values, pair selection (first max / first min, lowest position wins ties),
+ * gain = D1 + D2 - 2w, lock-and-swap, recompute of the neighbours' D-values; stops after
+ * floor(log2 N)+6 consecutive non-positive gains.  Replaces KL(), cKL.cpp:288-390 ; gKL.cu:417-549.
+ * trace may be NULL (the trace then stays on the device; swaps is reported in eigkl_stats).      */
+int  eigkl_kl_run(eigkl_handle *h, eigkl_trace *trace);
+/* Writes results/<base>_KL_CutSize[_EIG]_output.txt exactly as cKL.cpp:315,380 does.             */
+int  eigkl_write_trace(const char *path, const eigkl_trace *trace);
+/* current side of every node (after eigkl_kl_run: the final partition, which the reference never
+ * writes anywhere -- SURVEY.md section 8f.3)                                                     */
+int  eigkl_get_partition(eigkl_handle *h, uint8_t *side);
+
+/* ---- test / measurement hooks ------------------------------------------------------------------ */
+int  eigkl_spmv(eigkl_handle *h, const double *x, double *y);                 /* y = L x (host buffers) */
+int  eigkl_dvalues(eigkl_handle *h, float *val);       /* connections() for every node, cKL.cpp:225-251 */
+int  eigkl_cut(eigkl_handle *h, float *cut);           /* calCutSize() on one thread, cKL.cpp:199-223   */
+/* device copies of the assembled matrices (any pointer may be NULL); sizes from eigkl_get_stats   */
+int  eigkl_get_laplacian(eigkl_handle *h, int32_t *rowptr, int32_t *col, double *val);
+int  eigkl_get_kl_graph(eigkl_handle *h, int32_t *rowptr, int32_t *fwd_end, int32_t *col, float *w);
+/* runs `iters` back-to-back launches of one kernel class on resident data and returns the average
+ * device time per launch in ms (CUDA events on the handle's stream).  what: 0 = SpMV, 1 = D-values.
+ * flush_l2 != 0 writes a >L2 buffer between launches (excluded from the time).                   */
+int  eigkl_time_kernel(eigkl_handle *h, int what, int iters, int flush_l2, double *ms_avg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EIGKL_H */
