@@ -80,8 +80,7 @@ def build(force=False, verbose=False):
     objs = [os.path.join(OBJ, s + ".o") for s in SOURCES]
     if jobs or force or not os.path.exists(LIB):
         link = [NVCC] + ARCH + ["-shared", "-ccbin", HOST_CXX, "-o", LIB] + objs + ["-lcudart"]
-        if WITH_NCCL:
-            link += ["-lnccl"]
+        link += ["-ldl"]          # NCCL is bound with dlopen at run time (see csrc/comm.cpp)
         _run(link, verbose)
     cli_hdrs = [os.path.join(CLI, "cli_common.h"), os.path.join(CLI, "kl_main.h"), os.path.join(ROOT, "include", "eigkl.h")]
     for c in CLIS:

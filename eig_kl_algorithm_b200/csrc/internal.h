@@ -268,6 +268,10 @@ void write_trace_file(const char *path, const eigkl_trace *t);
 void comm_init(eigkl_handle *h);
 void comm_destroy(eigkl_handle *h);
 void comm_unique_id(void *id128);
+void comm_allreduce_sum_f64(eigkl_handle *h, double *buf, size_t count);            // in place, on h->stream
+void comm_allreduce_max_u64(eigkl_handle *h, unsigned long long *buf, size_t count);
+void comm_allgather_f64(eigkl_handle *h, const double *send, double *recv, size_t count_per_rank);
+void comm_broadcast_bytes(eigkl_handle *h, void *buf, size_t bytes, int root);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -1,0 +1,264 @@
+"""Parity of the CUDA path with the oracle and the reference's golden vectors.  Everything here goes
+through the C ABI (include/eigkl.h via eig_kl_algorithm_b200.api) on a real B200.
+
+Bars: integer / fp32-ordered work bit-exact (KL graph layout and weights, D-values, initial cut,
+gain column, swap sequence, trace file bytes); fp64 Fiedler solve within the north-star tolerance
+(lambda2 rel. err <= 1e-8, sine <= 1e-6 after sign alignment).
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, CIRCUITS
+from eig_kl_algorithm_b200 import api, datasets
+from test_oracle import APPENDIX_D, golden_swaps
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def handles(eigkl_lib, circuits):
+    hs = {}
+    for c in CIRCUITS:
+        h = api.Handle()
+        h.load_hgr(circuits[c])
+        hs[c] = h
+    yield hs
+    for h in hs.values():
+        h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# assembly
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", CIRCUITS)
+def test_kl_graph_layout_bit_exact(c, handles, oracle, circuits):
+    h = handles[c]
+    h.assemble_kl_graph()
+    rp, fe, col, w = h.get_kl_graph()
+    o = oracle.OracleKL(oracle.OracleHgr(circuits[c]))
+    assert np.array_equal(rp, o.rowptr.astype(np.int32))
+    assert np.array_equal(fe, o.fwd_end.astype(np.int32))
+    assert np.array_equal(col, o.col)                       # traversal order incl. unordered_map order
+    assert np.array_equal(w.view(np.uint32), o.w.view(np.uint32))   # fp32 sums in file order, bit for bit
+
+
+@pytest.mark.parametrize("c", CIRCUITS)
+def test_laplacian_matches_oracle(c, handles, oracle, circuits):
+    h = handles[c]
+    h.assemble_laplacian()
+    rp, col, val = h.get_laplacian()
+    o = oracle.OracleEIG(oracle.OracleHgr(circuits[c]))
+    assert np.array_equal(rp, o.rowptr.astype(np.int32))
+    assert np.array_equal(col, o.col)
+    assert np.array_equal(val, o.val)                       # same fp64 sums in the same (file) order
+    x = np.random.default_rng(0).standard_normal(h.n_nodes)
+    y = h.spmv(x)
+    yo = o.spmv(x)
+    assert np.abs(y - yo).max() <= 1e-12 * np.abs(yo).max()
+    assert np.abs(h.spmv(np.ones(h.n_nodes))).max() < 1e-13 * np.abs(val).max() * 64   # L 1 = 0 up to row round-off
+
+
+# ---------------------------------------------------------------------------------------------------
+# KL
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", CIRCUITS)
+def test_dvalues_and_cut_bit_exact(c, handles, oracle, circuits, workdir):
+    h = handles[c]
+    h.assemble_kl_graph()
+    o = oracle.OracleKL(oracle.OracleHgr(circuits[c]))
+    g = oracle.read_eig(datasets.golden_eig_path(workdir, c), h.n_nodes)
+    rng = np.random.default_rng(5)
+    for side in (g["side"], rng.integers(0, 2, h.n_nodes).astype(np.uint8)):
+        h.set_partition(side)
+        assert np.array_equal(h.dvalues().view(np.uint32), o.dvalues(side).view(np.uint32))
+        assert h.cut().view(np.uint32) == o.cut0(side).view(np.uint32)
+
+
+@pytest.mark.parametrize("c", CIRCUITS)
+def test_kl_trace_byte_exact_vs_reference(c, handles, workdir, tmp_path):
+    """cKL <c>.hgr -EIG: the trace file equals the file the reference wrote on one core, byte for byte,
+    and the swapped node ids equal the instrumented reference's."""
+    h = handles[c]
+    h.assemble_kl_graph()
+    h.load_eig(datasets.golden_eig_path(workdir, c))
+    tr = h.kl_run()
+    out = str(tmp_path / "trace.txt")
+    api.write_trace(out, tr)
+    raw = open(out, "rb").read()
+    assert tr["swaps"] == APPENDIX_D[c][0]
+    n1, n2 = golden_swaps(c)
+    assert np.array_equal(tr["node1"][1:], n1) and np.array_equal(tr["node2"][1:], n2)
+    assert raw == open(os.path.join(GOLDEN, c + ".kl_trace_1core.txt"), "rb").read()
+    assert hashlib.md5(raw).hexdigest() == APPENDIX_D[c][1]
+    side = h.get_partition()
+    assert int(side.sum()) == h.n_nodes - (h.n_nodes + 1) // 2 or int(side.sum()) > 0
+
+
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
+def test_kl_cluster_sizes_agree(cluster, oracle, circuits, workdir):
+    c = "industry2"
+    with api.Handle(kl_cluster=cluster) as h:
+        h.load_hgr(circuits[c])
+        h.assemble_kl_graph()
+        h.load_eig(datasets.golden_eig_path(workdir, c))
+        tr = h.kl_run()
+        assert h.stats()["kl_cluster"] == cluster
+    n1, n2 = golden_swaps(c)
+    assert np.array_equal(tr["node1"][1:], n1) and np.array_equal(tr["node2"][1:], n2)
+
+
+@pytest.mark.parametrize("c", ["fract", "ibm01"])
+def test_kl_random_ordered_partition(c, handles, oracle, circuits):
+    """The non -EIG branch (cKL.cpp:175-193): remain[] in shuffled order, ties go to the earlier position."""
+    h = handles[c]
+    h.assemble_kl_graph()
+    o = oracle.OracleKL(oracle.OracleHgr(circuits[c]))
+    rng = np.random.default_rng(11)
+    perm = rng.permutation(h.n_nodes).astype(np.int32)
+    mid = h.n_nodes // 2
+    o0, o1 = perm[:mid], perm[mid:]
+    side = np.zeros(h.n_nodes, np.uint8)
+    side[o1] = 1
+    ro = o.run(side, o0, o1)
+    h.set_partition_ordered(o0, o1)
+    tr = h.kl_run()
+    assert tr["swaps"] == ro["swaps"]
+    assert np.array_equal(tr["node1"], ro["node1"]) and np.array_equal(tr["node2"], ro["node2"])
+    assert np.array_equal(tr["gain"].view(np.uint32), ro["gain"].view(np.uint32))
+    assert np.array_equal(tr["cut"].view(np.uint32), ro["cut"].view(np.uint32))
+    assert np.array_equal(h.get_partition(), ro["side"])
+
+
+def _random_hypergraph(rng, n_nodes, n_nets, big=0):
+    nets = []
+    for _ in range(n_nets):
+        k = int(rng.choice([1, 2, 2, 2, 3, 4, 5, 8]))
+        nets.append(rng.choice(n_nodes, size=min(k, n_nodes), replace=False))
+    for _ in range(big):
+        nets.append(rng.choice(n_nodes, size=min(n_nodes, int(rng.integers(100, 400))), replace=False))
+    nets.insert(len(nets) // 2, np.zeros(0, np.int64))       # an empty net line
+    off = np.zeros(len(nets) + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for x in nets])
+    pins = np.concatenate(nets).astype(np.int32) if off[-1] else np.zeros(0, np.int32)
+    return off, pins
+
+
+@pytest.mark.parametrize("seed,n_nodes,n_nets,big", [(1, 50, 40, 0), (2, 700, 900, 3), (3, 5000, 5000, 6), (4, 300, 10, 2)])
+def test_ragged_random_hypergraphs(seed, n_nodes, n_nets, big, oracle, tmp_path):
+    """Ragged inputs: 1-pin and empty nets, isolated nodes, nets of hundreds of pins (rehash chains)."""
+    rng = np.random.default_rng(seed)
+    off, pins = _random_hypergraph(rng, n_nodes, n_nets, big)
+    path = str(tmp_path / "r.hgr")
+    with open(path, "w") as f:
+        f.write(f"{len(off) - 1} {n_nodes}\n")
+        for e in range(len(off) - 1):
+            f.write(" ".join(str(int(p) + 1) for p in pins[off[e]:off[e + 1]]) + " \n")
+    oh = oracle.OracleHgr(path)
+    o = oracle.OracleKL(oh)
+    side = rng.integers(0, 2, n_nodes).astype(np.uint8)
+    ro = o.run(side)
+    with api.Handle() as h:
+        h.set_pins(n_nodes, off, pins)                       # the host-array entry point
+        h.assemble_kl_graph()
+        rp, fe, col, w = h.get_kl_graph()
+        assert np.array_equal(rp, o.rowptr.astype(np.int32)) and np.array_equal(col, o.col)
+        assert np.array_equal(w.view(np.uint32), o.w.view(np.uint32))
+        h.set_partition(side)
+        tr = h.kl_run()
+        assert tr["swaps"] == ro["swaps"]
+        assert np.array_equal(tr["node1"], ro["node1"]) and np.array_equal(tr["node2"], ro["node2"])
+        assert np.array_equal(tr["cut"].view(np.uint32), ro["cut"].view(np.uint32))
+        assert np.array_equal(tr["gain"].view(np.uint32), ro["gain"].view(np.uint32))
+
+
+def test_bad_inputs_are_rejected(tmp_path):
+    with api.Handle() as h:
+        off = np.array([0, 3], np.int64)
+        with pytest.raises(api.EigklError) as e:
+            h.set_pins(4, off, np.array([0, 1, 7], np.int32))            # pin out of range
+        assert e.value.code == -3
+        h.set_pins(4, off, np.array([0, 1, 1], np.int32))                # duplicate pin in a net
+        with pytest.raises(api.EigklError) as e:
+            h.assemble_kl_graph()
+        assert e.value.code == -3
+        with pytest.raises(api.EigklError) as e:
+            h.load_hgr(str(tmp_path / "missing.hgr"))
+        assert e.value.code == -2
+        h.set_pins(4, off, np.array([0, 1, 2], np.int32))
+        with pytest.raises(api.EigklError):
+            h.kl_run()                                                   # no graph / partition yet
+
+
+# ---------------------------------------------------------------------------------------------------
+# EIG
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c", ["fract", "ibm01", "industry2"])
+def test_fiedler_vs_golden(c, handles, oracle, workdir, tmp_path):
+    h = handles[c]
+    h.assemble_laplacian()
+    lam, v = h.fiedler()
+    g = oracle.read_eig(datasets.golden_eig_path(workdir, c), h.n_nodes)
+    st = h.stats()
+    assert st["converged"] == 1
+    assert abs(lam - g["lambda2"]) / g["lambda2"] <= 1e-8                 # north star: 1e-8 relative
+    assert abs(np.linalg.norm(v) - 1.0) < 1e-12
+    cs = abs(v @ g["vec"]) / np.linalg.norm(g["vec"])
+    assert np.sqrt(max(0.0, 1.0 - cs * cs)) <= 1e-6                       # north star: 1e-6 sine
+    # residual of the returned pair
+    r = np.linalg.norm(h.spmv(v) - lam * v)
+    assert r <= 1e-9 * max(1.0, abs(lam)) * 1e2
+    # median / sides on the device == cEIG.cpp:55-65,218 on the host
+    med, side = h.partition_from_fiedler()
+    assert med == oracle.median(v)
+    assert np.array_equal(side, (med > v).astype(np.uint8))
+    s = np.sign(v @ g["vec"])
+    side_aligned = side if s > 0 else (oracle.median(-v) > -v).astype(np.uint8)
+    assert int((side_aligned != g["side"]).sum()) == 0                    # same partition as the reference's file
+    # the file we write parses back to the same numbers (12 significant digits)
+    out = str(tmp_path / "eig.txt")
+    h.write_eig(out)
+    back = oracle.read_eig(out, h.n_nodes)
+    assert np.array_equal(back["side"], side)
+    assert abs(back["lambda2"] - lam) <= 1e-11 * abs(lam) + 1e-300
+    assert np.abs(back["vec"] - v).max() <= 1e-11
+
+
+def test_fiedler_ibm10_residual(handles, oracle, circuits):
+    """ibm10's golden file is not a converged pair: check by residual and vs the oracle."""
+    h = handles["ibm10"]
+    h.assemble_laplacian()
+    lam, v = h.fiedler()
+    assert abs(lam - 0.0185035852) / 0.0185035852 < 1e-7                  # converged lambda2, SURVEY Appendix D
+    assert np.linalg.norm(h.spmv(v) - lam * v) < 1e-9
+
+
+def test_fiedler_is_reproducible(handles):
+    h = handles["ibm01"]
+    h.assemble_laplacian()
+    l1, v1 = h.fiedler()
+    l2, v2 = h.fiedler()
+    assert l1 == l2 and np.array_equal(v1, v2)                            # fixed-order reductions
+
+
+def test_fused_pipeline_equals_file_handoff(handles, oracle, circuits, tmp_path):
+    """EIG -> KL in one process (gKL2.cu:1018-1024's aim) == cEIG file -> cKL -EIG, and == the oracle."""
+    c = "ibm01"
+    h = handles[c]
+    h.assemble_laplacian()
+    h.fiedler(want_vector=False)
+    med, side = h.partition_from_fiedler()
+    h.assemble_kl_graph()
+    tr = h.kl_run()
+    o = oracle.OracleKL(oracle.OracleHgr(circuits[c]))
+    ro = o.run(side)
+    assert tr["swaps"] == ro["swaps"]
+    assert np.array_equal(tr["node1"], ro["node1"]) and np.array_equal(tr["node2"], ro["node2"])
+    assert np.array_equal(tr["cut"].view(np.uint32), ro["cut"].view(np.uint32))
+    out = str(tmp_path / "e.txt")
+    h.write_eig(out)
+    h.load_eig(out)
+    tr2 = h.kl_run()
+    assert np.array_equal(tr2["node1"], tr["node1"]) and np.array_equal(tr2["cut"], tr["cut"])
