@@ -22,6 +22,7 @@ ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_FORMAT", -4: "E_CUDA", -5: "E
 SYMBOLS = [
     "eigkl_abi_version", "eigkl_nccl_unique_id", "eigkl_create", "eigkl_destroy", "eigkl_last_error",
     "eigkl_get_stats", "eigkl_synchronize", "eigkl_load_hgr", "eigkl_set_pins", "eigkl_get_sizes",
+    "eigkl_invalidate", "eigkl_get_stream",
     "eigkl_assemble_laplacian", "eigkl_fiedler", "eigkl_partition_from_fiedler", "eigkl_write_eig",
     "eigkl_assemble_kl_graph", "eigkl_set_partition", "eigkl_set_partition_ordered", "eigkl_load_eig",
     "eigkl_kl_run", "eigkl_write_trace", "eigkl_get_partition", "eigkl_spmv", "eigkl_dvalues", "eigkl_cut",
@@ -98,6 +99,8 @@ def load_library(path=LIB_PATH):
     L.eigkl_load_hgr.argtypes = [H, C.c_char_p]
     L.eigkl_set_pins.argtypes = [H, C.c_int32, C.c_int32, P(C.c_int64), P(C.c_int32)]
     L.eigkl_get_sizes.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_int64)]
+    L.eigkl_invalidate.argtypes = [H]
+    L.eigkl_get_stream.argtypes = [H, P(C.c_void_p)]
     L.eigkl_assemble_laplacian.argtypes = [H]
     L.eigkl_fiedler.argtypes = [H, P(C.c_double), P(C.c_double)]
     L.eigkl_partition_from_fiedler.argtypes = [H, P(C.c_double), P(C.c_uint8)]
@@ -188,6 +191,20 @@ class Handle:
         a, b, c = C.c_int32(), C.c_int32(), C.c_int64()
         self._check(self.lib.eigkl_get_sizes(self._h, C.byref(a), C.byref(b), C.byref(c)))
         self.n_nodes, self.n_nets, self.n_pins = a.value, b.value, c.value
+
+    def set_pins_ptr(self, n_nodes, n_nets, net_off_ptr, pins_ptr):
+        """Same as set_pins with raw host addresses (e.g. pinned torch tensors' data_ptr())."""
+        self._check(self.lib.eigkl_set_pins(self._h, n_nodes, n_nets, C.cast(net_off_ptr, C.POINTER(C.c_int64)),
+                                            C.cast(pins_ptr, C.POINTER(C.c_int32))))
+        self._sizes()
+
+    def invalidate(self):
+        self._check(self.lib.eigkl_invalidate(self._h))
+
+    def stream_ptr(self):
+        s = C.c_void_p()
+        self._check(self.lib.eigkl_get_stream(self._h, C.byref(s)))
+        return s.value or 0
 
     # ---- EIG ----------------------------------------------------------------------------------------
     def assemble_laplacian(self):

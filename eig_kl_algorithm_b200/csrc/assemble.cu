@@ -136,10 +136,10 @@ void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t
   EIGKL_REQUIRE(net_off[0] == 0, EIGKL_E_ARG, "eigkl_set_pins: net_off[0] must be 0");
   const int64_t n_pins = net_off[n_nets];
   auto &g = h->hg;
-  g = Hypergraph();
-  h->ue = UniqueEdges();
-  h->L = LaplacianCsr();
-  h->A = KlCsr();
+  g.loaded = false;
+  h->ue.valid = false;
+  h->L.valid = false;
+  h->A.valid = false;
   h->kl.have_partition = false;
   h->eig.have_vector = h->eig.have_median = false;
   g.n_nodes = n_nodes; g.n_nets = n_nets; g.n_pins = n_pins;
@@ -148,7 +148,7 @@ void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t
   g.pair_off.alloc((size_t)n_nets + 1);
   EIGKL_CUDA(cudaMemcpyAsync(g.net_off.p, net_off, ((size_t)n_nets + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, h->stream));
   if (n_pins) EIGKL_CUDA(cudaMemcpyAsync(g.pins.p, pins, (size_t)n_pins * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
-  DBuf<int> err; err.alloc(1);
+  auto &err = h->scr.err; err.alloc(1);
   EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
   if (n_pins) { validate_pins_kernel<<<grid_for(n_pins), TPB, 0, h->stream>>>(g.pins.p, n_pins, n_nodes, err.p); h->launches++; }
   if (n_nets) { net_pair_count_kernel<<<grid_for(n_nets), TPB, 0, h->stream>>>(g.net_off.p, n_nets, g.pair_off.p); h->launches++; }
@@ -177,14 +177,14 @@ void build_unique_edges(eigkl_handle *h) {
   for (int i = 0; i < 2; ++i) { e.sortkey[i].ensure((size_t)std::max<int64_t>(P, n) + 1); e.sortval[i].ensure((size_t)std::max<int64_t>(P, n) + 1); }
   unsigned long long *keys[2] = {e.sortkey[0].p, e.sortkey[1].p};
   uint32_t *vals[2] = {e.sortval[0].p, e.sortval[1].p};
-  DBuf<int> err; err.alloc(1);
+  auto &err = h->scr.err; err.alloc(1);
   EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
   int64_t U = 0;
   if (P > 0) {
     expand_pairs_kernel<<<grid_for(P), TPB, 0, h->stream>>>(g.net_off.p, g.pins.p, g.pair_off.p, g.n_nets, P, nb, keys[0], vals[0], err.p);
     h->launches++;
     const int cur = radix_sort_kv(h, keys, vals, P, 2 * nb);
-    DBuf<int32_t> flag; flag.alloc((size_t)P + 1);
+    auto &flag = h->scr.i32a; flag.alloc((size_t)P + 1);
     head_flag_kernel<<<grid_for(P), TPB, 0, h->stream>>>(keys[cur], P, flag.p);
     h->launches++;
     exclusive_scan_i32(h, flag.p, flag.p, P);
@@ -198,7 +198,6 @@ void build_unique_edges(eigkl_handle *h) {
     segment_reduce_kernel<<<grid_for(P), TPB, 0, h->stream>>>(keys[cur], vals[cur], flag.p, P, nb, g.net_off.p, g.pair_off.p,
                                                              g.n_nets, ue.a.p, ue.b.p, ue.wA.p, ue.wL.p, ue.first.p);
     h->launches++;
-    EIGKL_CUDA(cudaStreamSynchronize(h->stream));   // flag is freed at scope exit
   }
   ue.U = U;
   ue.fstart.alloc((size_t)n + 1);
@@ -211,11 +210,10 @@ void build_unique_edges(eigkl_handle *h) {
     h->launches++;
     const int cur = radix_sort_kv(h, keys, vals, U, nb);
     EIGKL_CUDA(cudaMemcpyAsync(ue.perm_b.p, vals[cur], (size_t)U * sizeof(uint32_t), cudaMemcpyDeviceToDevice, h->stream));
-    DBuf<int32_t> bs; bs.alloc((size_t)U);
+    auto &bs = h->scr.i32b; bs.alloc((size_t)U);
     keys_to_i32_kernel<<<grid_for(U), TPB, 0, h->stream>>>(keys[cur], U, bs.p);
     lower_bound_kernel<<<grid_for(n + 1), TPB, 0, h->stream>>>(bs.p, U, n, ue.bstart.p);
     h->launches += 2;
-    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   } else {
     EIGKL_CUDA(cudaMemsetAsync(ue.bstart.p, 0, ((size_t)n + 1) * sizeof(int32_t), h->stream));
   }
@@ -289,7 +287,7 @@ void assemble_laplacian(eigkl_handle *h) {
   auto &L = h->L;
   const int32_t n = h->hg.n_nodes;
   const int64_t U = ue.U;
-  L = LaplacianCsr();
+  L.valid = false;
   L.n = n;
   L.nnz = 2 * U + n;
   EIGKL_REQUIRE(L.nnz < (int64_t)2147483647, EIGKL_E_ARG, "Laplacian has more than 2^31-1 non-zeros");
@@ -383,7 +381,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   auto &A = h->A;
   const int32_t n = h->hg.n_nodes;
   const int64_t U = ue.U;
-  A = KlCsr();
+  A.valid = false;
   A.n = n;
   A.nnz = 2 * U;
   EIGKL_REQUIRE(A.nnz < (int64_t)2147483647, EIGKL_E_ARG, "KL graph has more than 2^31-1 entries");
@@ -391,7 +389,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   A.fwd_end.alloc((size_t)n);
   A.col.alloc((size_t)A.nnz);
   A.w.alloc((size_t)A.nnz);
-  DBuf<int32_t> soff; soff.alloc((size_t)n + 1);
+  auto &soff = h->scr.i32a; soff.alloc((size_t)n + 1);
   kl_degree_kernel<<<grid_for(n), TPB, 0, h->stream>>>(ue.fstart.p, ue.bstart.p, n, A.rowptr.p, soff.p);
   h->launches++;
   exclusive_scan_i32(h, A.rowptr.p, A.rowptr.p, n);
@@ -399,7 +397,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   int32_t scratch_total = 0;
   EIGKL_CUDA(cudaMemcpyAsync(&scratch_total, soff.p + n, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
-  DBuf<int32_t> scratch; scratch.alloc((size_t)scratch_total + 1);
+  auto &scratch = h->scr.i32b; scratch.alloc((size_t)scratch_total + 1);
   if (U > 0) {
     auto &e = h->eig;
     unsigned long long *keys[2] = {e.sortkey[0].p, e.sortkey[1].p};
@@ -421,7 +419,6 @@ void assemble_kl_graph(eigkl_handle *h) {
   row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, n, KLD_CHUNK, A.n_blocks, A.blk_row.p);
   h->launches++;
   EIGKL_CUDA(cudaGetLastError());
-  EIGKL_CUDA(cudaStreamSynchronize(h->stream));    // scratch / soff are freed at scope exit
   A.valid = true;
   h->stats.nnz_kl = A.nnz;
   // algorithmic bytes of one full D-value pass: nnz*(4 w + 4 col) + n*(4 rowptr + 1 side + 4 out)  

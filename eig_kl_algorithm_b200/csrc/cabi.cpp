@@ -198,6 +198,25 @@ int eigkl_get_sizes(const eigkl_handle *h, int32_t *n_nodes, int32_t *n_nets, in
   return EIGKL_OK;
 }
 
+int eigkl_invalidate(eigkl_handle *h) {
+  return guarded(h, [&] {
+    EIGKL_REQUIRE(h->hg.loaded, EIGKL_E_ARG, "eigkl_invalidate: no hypergraph loaded");
+    EIGKL_CUDA(cudaSetDevice(h->device));
+    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+    h->ue.valid = false;
+    h->L.valid = false;
+    h->A.valid = false;
+    h->kl.have_partition = false;
+    h->eig.have_vector = h->eig.have_median = false;
+  });
+}
+
+int eigkl_get_stream(const eigkl_handle *h, void **stream) {
+  if (!h || !stream) return EIGKL_E_ARG;
+  *stream = (void *)h->stream;
+  return EIGKL_OK;
+}
+
 int eigkl_assemble_laplacian(eigkl_handle *h) {
   return guarded(h, [&] {
     EIGKL_CUDA(cudaSetDevice(h->device));

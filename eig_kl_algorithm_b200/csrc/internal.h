@@ -47,13 +47,16 @@ struct DBuf {
     if (p) cudaFree(p);
     p = nullptr; n = 0;
   }
+  // grow-only: device allocations are never returned inside the hot path (cudaFree synchronises the
+  // device and cudaMalloc costs 0.1-100 ms, more than a whole assembly stage)
   void alloc(size_t count) {
-    release();
     if (count == 0) count = 1;
+    if (count <= n) return;
+    release();
     EIGKL_CUDA(cudaMalloc((void **)&p, count * sizeof(T)));
     n = count;
   }
-  void ensure(size_t count) { if (count > n) alloc(count); }
+  void ensure(size_t count) { alloc(count); }
   size_t bytes() const { return n * sizeof(T); }
 };
 
@@ -218,6 +221,13 @@ struct eigkl_handle {
   // scratch of the sort / scan primitives
   eigkl::DBuf<int32_t> sort_hist;
   eigkl::DBuf<int64_t> scan_tmp;
+  // stage-local temporaries (grow-only, reused across calls; stream order keeps reuse safe)
+  struct {
+    eigkl::DBuf<int32_t> i32a, i32b;
+    eigkl::DBuf<uint32_t> u32a, u32b;
+    eigkl::DBuf<uint8_t> u8a;
+    eigkl::DBuf<int> err;
+  } scr;
   int64_t launches = 0;
 };
 

@@ -180,8 +180,8 @@ void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
   const int32_t n = h->hg.n_nodes;
   auto &k = h->kl;
   kl_alloc_state(h, n);
-  DBuf<int32_t> pos; pos.alloc((size_t)n + 1);
-  DBuf<int> err; err.alloc(1);
+  auto &pos = h->scr.i32a; pos.alloc((size_t)n + 1);
+  auto &err = h->scr.err; err.alloc(1);
   EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
   side_flag_kernel<<<grid_for(n), TPB, 0, h->stream>>>(side_dev, n, pos.p, err.p);
   exclusive_scan_i32(h, pos.p, pos.p, n);
@@ -202,15 +202,15 @@ void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *
   auto &k = h->kl;
   if (ascending) {
     EIGKL_REQUIRE(side_host != nullptr, EIGKL_E_ARG, "side is NULL");
-    DBuf<uint8_t> side; side.alloc((size_t)n);
+    auto &side = h->scr.u8a; side.alloc((size_t)n);
     EIGKL_CUDA(cudaMemcpyAsync(side.p, side_host, (size_t)n, cudaMemcpyHostToDevice, h->stream));
     kl_set_partition_device(h, side.p);
     return;
   }
   EIGKL_REQUIRE(order0 && order1 && n0 >= 0 && n1 >= 0 && n0 + n1 == n, EIGKL_E_ARG, "orders must cover every node once");
   kl_alloc_state(h, n);
-  DBuf<int32_t> seen; seen.alloc((size_t)n);
-  DBuf<int> err; err.alloc(1);
+  auto &seen = h->scr.i32a; seen.alloc((size_t)n);
+  auto &err = h->scr.err; err.alloc(1);
   EIGKL_CUDA(cudaMemsetAsync(seen.p, 0, (size_t)n * sizeof(int32_t), h->stream));
   EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
   EIGKL_CUDA(cudaMemcpyAsync(k.order0.p, order0, (size_t)n0 * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
@@ -298,12 +298,12 @@ float kl_cut0(eigkl_handle *h) {
   for (int i = 0; i < 2; ++i) { e.sortkey[i].ensure(need); e.sortval[i].ensure(need); }
   unsigned long long *keys[2] = {e.sortkey[0].p, e.sortkey[1].p};
   uint32_t *vals[2] = {e.sortval[0].p, e.sortval[1].p};
-  DBuf<uint32_t> set_rank; set_rank.alloc((size_t)n);
-  DBuf<int32_t> seq; seq.alloc((size_t)std::max(n1, 1));
+  auto &set_rank = h->scr.u32a; set_rank.alloc((size_t)n);
+  auto &seq = h->scr.i32a; seq.alloc((size_t)std::max(n1, 1));
   // (1) iteration order of unordered_set<uint32_t>(remain[1].begin(), remain[1].end())
   if (n1 > 0) {
     const uint32_t Bfinal = stl_final_buckets((uint32_t)n1);
-    DBuf<uint32_t> first; first.alloc(Bfinal);
+    auto &first = h->scr.u32b; first.alloc(Bfinal);
     int32_t done = 0;                                   // elements already in seq
     for (int lv = 0; lv < STL_CHAIN_LEN; ++lv) {
       const uint32_t B = stl_bucket_chain(lv);

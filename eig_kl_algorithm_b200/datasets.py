@@ -89,3 +89,23 @@ def write_synthetic(path, scale, seed=12345):
         f.write("".join(" ".join(map(str, net)) + "\n" for net in nets))
     os.replace(tmp, path)
     return path
+
+
+def read_hgr_arrays(path):
+    """Host-side .hgr reader for callers of eigkl_set_pins: returns (n_nodes, net_off int64, pins int32).
+
+    Same reading rules as the library's own parser (csrc/hgr_io.cpp): header "<nets> <nodes>", then
+    exactly <nets> lines of 1-based ids; missing lines are empty nets.
+    """
+    import numpy as np
+    with open(path, "rb") as f:
+        header = f.readline().split()
+        n_nets, n_nodes = int(header[0]), int(header[1])
+        lines = f.read().split(b"\n")
+    lines = lines[:n_nets] + [b""] * max(0, n_nets - len(lines))
+    counts = np.fromiter((len(l.split()) for l in lines), dtype=np.int64, count=n_nets)
+    net_off = np.zeros(n_nets + 1, np.int64)
+    np.cumsum(counts, out=net_off[1:])
+    pins = np.array(b" ".join(lines).split(), dtype=np.int64) - 1
+    assert len(pins) == net_off[-1]
+    return n_nodes, net_off, pins.astype(np.int32)

@@ -113,6 +113,12 @@ int  eigkl_load_hgr(eigkl_handle *h, const char *path);
 int  eigkl_set_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets,
                     const int64_t *net_off, const int32_t *pins);
 int  eigkl_get_sizes(const eigkl_handle *h, int32_t *n_nodes, int32_t *n_nets, int64_t *n_pins);
+/* Drops everything derived from the pins (assembled matrices, Fiedler vector, partition) but keeps the
+ * pins resident in HBM, so that the next eigkl_assemble_* call redoes the sort + segmented reduce.   */
+int  eigkl_invalidate(eigkl_handle *h);
+/* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, for callers that want to
+ * record their own events around calls.                                                              */
+int  eigkl_get_stream(const eigkl_handle *h, void **stream);
 
 /* ---- EIG stage (the cEIG executable) ---------------------------------------------------------- */
 /* Clique-model Laplacian L = D - A, A_ij = sum over nets containing i and j of 2.0/|net| (fp64), as a

@@ -575,13 +575,22 @@ static double orc_dot(const double *a, const double *b, int32_t n) {
   for (int32_t i = 0; i < n; ++i) s += a[i] * b[i];
   return s;
 }
+static int orc_fiedler_impl(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *st, int maxit_override);
 int orc_fiedler(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *st) {
+  return orc_fiedler_impl(L, lambda2, vec, st, 0);
+}
+/* bounded sample for bench.py's cpu_baseline: stops after max_restarts restart cycles (st->converged
+ * tells whether that was enough); st->matvecs is the work actually done */
+int orc_fiedler_bounded(const orc_csr *L, int max_restarts, double *lambda2, double *vec, orc_eig_stats *st) {
+  return orc_fiedler_impl(L, lambda2, vec, st, max_restarts);
+}
+static int orc_fiedler_impl(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *st, int maxit_override) {
   const int32_t n = L->n;
   const int nev = 2;
   int m = n / 2 < 100 ? n / 2 : 100;                               /* cEIG.cpp:195 */
   if (m <= nev || m > n) return -3;
   const double tol = 1e-10, eps23 = pow(DBL_EPSILON, 2.0 / 3.0);
-  const int maxit = 1000;
+  const int maxit = maxit_override > 0 ? maxit_override : 1000;
   double *V = (double *)malloc((size_t)n * (size_t)(m + 1) * sizeof(double));
   double *T = (double *)calloc((size_t)m * m, sizeof(double));
   double *Y = (double *)malloc((size_t)m * m * sizeof(double));
@@ -590,6 +599,12 @@ int orc_fiedler(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *s
   double *h2 = (double *)malloc((size_t)(m + 1) * sizeof(double));
   double *w = (double *)malloc((size_t)n * sizeof(double));
   double *Vk = (double *)malloc((size_t)n * (size_t)(m) * sizeof(double));
+#ifdef _OPENMP
+  const int max_threads = omp_get_max_threads();
+#else
+  const int max_threads = 1;
+#endif
+  double *part = (double *)malloc((size_t)max_threads * (size_t)(m + 1) * sizeof(double));
 #define VC(j) (V + (size_t)(j) * n)
   /* deterministic start vector: splitmix64 uniform in [-0.5, 0.5) */
   uint64_t sm = 0x9E3779B97F4A7C15ull;
@@ -610,17 +625,43 @@ int orc_fiedler(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *s
       orc_spmv(L, VC(j), w); ++nmv;
       for (int pass = 0; pass < 2; ++pass) {
         double *hh = pass ? h2 : h;
-#pragma omp parallel for schedule(static)
-        for (int c = 0; c <= j; ++c) {
-          double s = 0.0; const double *vc = VC(c);
-          for (int32_t i = 0; i < n; ++i) s += vc[i] * w[i];
-          hh[c] = s;
-        }
-#pragma omp parallel for schedule(static)
-        for (int32_t i = 0; i < n; ++i) {
-          double s = w[i];
-          for (int c = 0; c <= j; ++c) s -= VC(c)[i] * hh[c];
-          w[i] = s;
+        const int nc = j + 1;
+        /* hh = V^T w : every thread owns a contiguous row chunk (cache-blocked), partials folded in order */
+#pragma omp parallel
+        {
+#ifdef _OPENMP
+          const int nt = omp_get_num_threads(), tn = omp_get_thread_num();
+#else
+          const int nt = 1, tn = 0;
+#endif
+          const int64_t lo = (int64_t)n * tn / nt, hi = (int64_t)n * (tn + 1) / nt;
+          double *pp = part + (size_t)tn * (m + 1);
+          for (int c = 0; c < nc; ++c) pp[c] = 0.0;
+          for (int64_t b0 = lo; b0 < hi; b0 += 2048) {
+            const int64_t b1 = b0 + 2048 < hi ? b0 + 2048 : hi;
+            for (int c = 0; c < nc; ++c) {
+              const double *vc = VC(c);
+              double s = 0.0;
+              for (int64_t i = b0; i < b1; ++i) s += vc[i] * w[i];
+              pp[c] += s;
+            }
+          }
+#pragma omp barrier
+#pragma omp for schedule(static)
+          for (int c = 0; c < nc; ++c) {
+            double s = 0.0;
+            for (int t = 0; t < nt; ++t) s += part[(size_t)t * (m + 1) + c];
+            hh[c] = s;
+          }
+          /* w -= V hh */
+          for (int64_t b0 = lo; b0 < hi; b0 += 2048) {
+            const int64_t b1 = b0 + 2048 < hi ? b0 + 2048 : hi;
+            for (int c = 0; c < nc; ++c) {
+              const double *vc = VC(c);
+              const double hc = hh[c];
+              for (int64_t i = b0; i < b1; ++i) w[i] -= vc[i] * hc;
+            }
+          }
         }
       }
       T[(size_t)j * m + j] = h[j] + h2[j];
@@ -641,12 +682,18 @@ int orc_fiedler(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *s
     if (kk > m - 1) kk = m - 1;
     /* V[:, 0:kk] = V[:, 0:m] * Y[:, 0:kk] ; V[:, kk] = v_{m} */
 #pragma omp parallel for schedule(static)
-    for (int32_t i = 0; i < n; ++i)
+    for (int64_t b0 = 0; b0 < n; b0 += 1024) {
+      const int64_t b1 = b0 + 1024 < n ? b0 + 1024 : n;
       for (int c = 0; c < kk; ++c) {
-        double s = 0.0;
-        for (int j = 0; j < m; ++j) s += VC(j)[i] * Y[(size_t)j * m + c];
-        Vk[(size_t)c * n + i] = s;
+        double *out = Vk + (size_t)c * n;
+        for (int64_t i = b0; i < b1; ++i) out[i] = 0.0;
+        for (int j = 0; j < m; ++j) {
+          const double y = Y[(size_t)j * m + c];
+          const double *vj = VC(j);
+          for (int64_t i = b0; i < b1; ++i) out[i] += vj[i] * y;
+        }
       }
+    }
     memcpy(V, Vk, (size_t)n * kk * sizeof(double));
     memcpy(VC(kk), VC(m), (size_t)n * sizeof(double));
     memset(T, 0, (size_t)m * m * sizeof(double));
@@ -674,7 +721,7 @@ int orc_fiedler(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *s
     st->resid_est[0] = res[0]; st->resid_est[1] = res[1];
   }
 #undef VC
-  free(V); free(T); free(Y); free(th); free(h); free(h2); free(w); free(Vk);
+  free(V); free(T); free(Y); free(th); free(h); free(h2); free(w); free(Vk); free(part);
   return 0;
 }
 

@@ -74,6 +74,7 @@ typedef struct {
 } orc_eig_stats;
 /* two algebraically smallest eigenpairs; returns the larger one (lambda2) and its unit vector */
 int    orc_fiedler(const orc_csr *L, double *lambda2, double *vec, orc_eig_stats *st);
+int    orc_fiedler_bounded(const orc_csr *L, int max_restarts, double *lambda2, double *vec, orc_eig_stats *st);
 double orc_median(const double *v, int32_t n);                 /* cEIG.cpp:55-65 */
 /* writes the cEIG output format (cEIG.cpp:213-220) */
 int    orc_write_eig(const char *path, double lambda2, const double *vec, int32_t n);

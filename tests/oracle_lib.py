@@ -65,6 +65,7 @@ def lib():
         L.orc_csr_free.argtypes = [P(Csr)]
         L.orc_spmv.argtypes = [P(Csr), P(C.c_double), P(C.c_double)]
         L.orc_fiedler.argtypes = [P(Csr), P(C.c_double), P(C.c_double), P(EigStats)]
+        L.orc_fiedler_bounded.argtypes = [P(Csr), C.c_int, P(C.c_double), P(C.c_double), P(EigStats)]
         L.orc_median.argtypes = [P(C.c_double), C.c_int32]
         L.orc_median.restype = C.c_double
         L.orc_write_eig.argtypes = [C.c_char_p, C.c_double, P(C.c_double), C.c_int32]
@@ -179,11 +180,11 @@ class OracleEIG:
         lib().orc_spmv(C.byref(self.L), _p(x, C.c_double), _p(y, C.c_double))
         return y
 
-    def fiedler(self):
+    def fiedler(self, max_restarts=0):
         lam = C.c_double()
         vec = np.empty(self.n, np.float64)
         st = EigStats()
-        rc = lib().orc_fiedler(C.byref(self.L), C.byref(lam), _p(vec, C.c_double), C.byref(st))
+        rc = lib().orc_fiedler_bounded(C.byref(self.L), max_restarts, C.byref(lam), _p(vec, C.c_double), C.byref(st))
         if rc != 0:
             raise RuntimeError(f"orc_fiedler -> {rc}")
         return lam.value, vec, dict(matvecs=st.matvecs, restarts=st.restarts, converged=st.converged, ncv=st.ncv,
