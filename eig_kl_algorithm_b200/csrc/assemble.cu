@@ -15,6 +15,7 @@
 #include "internal.h"
 #include "device_utils.cuh"
 #include "stl_order.h"
+#include <algorithm>
 
 namespace eigkl {
 
@@ -278,8 +279,16 @@ __global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t n,
   blk_row[b] = lo;
 }
 
-constexpr int64_t SPMV_CHUNK = 2048;     // must match spmv.cu
-constexpr int64_t KLD_CHUNK = 2048;      // must match kl.cu
+// Row-block size in non-zeros.  The circuits here are small next to a B200 (ibm01: 0.23 M non-zeros vs
+// 0.3 M resident threads), so the kernels are latency bound: the chunk is sized to spread the matrix
+// over ~8 CTAs of 256 threads per SM in ONE wave, between 256 and 2048 non-zeros (the staging
+// capacities in spmv.cu / kl.cu are 4096).
+static int64_t pick_chunk(const eigkl_handle *h, int64_t nnz) {
+  const int64_t target_ctas = (int64_t)h->sm_count * 8;
+  int64_t c = ceil_div(std::max<int64_t>(nnz, 1), target_ctas);
+  c = ceil_div(c, 256) * 256;
+  return std::min<int64_t>(2048, std::max<int64_t>(256, c));
+}
 
 void assemble_laplacian(eigkl_handle *h) {
   build_unique_edges(h);
@@ -303,9 +312,10 @@ void assemble_laplacian(eigkl_handle *h) {
     h->launches += 2;
   }
   lap_diag_kernel<<<grid_for(n), TPB, 0, h->stream>>>(L.rowptr.p, ue.bstart.p, n, L.col.p, L.val.p);
-  L.n_blocks = (int32_t)ceil_div(L.nnz, SPMV_CHUNK);
+  const int64_t chunk = pick_chunk(h, L.nnz);
+  L.n_blocks = (int32_t)ceil_div(L.nnz, chunk);
   L.blk_row.alloc((size_t)L.n_blocks + 1);
-  row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, n, SPMV_CHUNK, L.n_blocks, L.blk_row.p);
+  row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, n, chunk, L.n_blocks, L.blk_row.p);
   h->launches += 2;
   EIGKL_CUDA(cudaGetLastError());
   L.valid = true;
@@ -414,9 +424,10 @@ void assemble_kl_graph(eigkl_handle *h) {
   } else {
     EIGKL_CUDA(cudaMemsetAsync(A.fwd_end.p, 0, (size_t)n * sizeof(int32_t), h->stream));
   }
-  A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz, KLD_CHUNK));
+  const int64_t chunk = pick_chunk(h, A.nnz);
+  A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz, chunk));
   A.blk_row.alloc((size_t)A.n_blocks + 1);
-  row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, n, KLD_CHUNK, A.n_blocks, A.blk_row.p);
+  row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, n, chunk, A.n_blocks, A.blk_row.p);
   h->launches++;
   EIGKL_CUDA(cudaGetLastError());
   A.valid = true;

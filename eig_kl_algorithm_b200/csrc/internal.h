@@ -216,6 +216,7 @@ struct eigkl_handle {
   eigkl::KlCsr A;
   eigkl::KlState kl;
   eigkl::EigState eig;
+  int spmv_mode = 0;           // EIGKL_SPMV_MODE: 0 auto, 1 stream, 2 vector (tuning aid)
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
   // scratch of the sort / scan primitives

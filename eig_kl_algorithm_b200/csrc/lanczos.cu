@@ -56,49 +56,77 @@ __device__ __forceinline__ double block_sum_256(double v, double *sm /* 8 double
   return r;
 }
 
-// h[c] = sum_i V[c*ld + i] * w[i], c in [0, ncols).  grid = (row chunks, column groups).
-// partial[bx * pstride + c]; the last CTA to finish (ticket counter) folds partials in bx order.
-// pass 2 additionally writes alpha[j] = h1[j] + h2[j].
+// h[c] = sum_i V[c*ld + i] * w[i], c in [0, ncols).
+// grid = (row chunks of MD_ROWS, column groups of MD_COLS): every thread owns two adjacent rows (one
+// 16-byte load per column) and MD_COLS columns, so a step with j columns exposes n/2 * j/8 threads with
+// 9 independent loads each -- enough bytes in flight to cover the L2/HBM latency even at n = 12 K.
+// partial[c * nbx + bx]; the last CTA of a column group (ticket counter per group) folds that group's
+// partials, one warp per column, in a fixed order.  pass 2 additionally writes alpha[j] = h1[j] + h2[j].
+constexpr int MD_ROWS = 2 * LZ_THREADS;
 __global__ void __launch_bounds__(LZ_THREADS)
 multidot_kernel(const double *__restrict__ V, size_t ld, int ncols, const double *__restrict__ w, int32_t n,
-                double *__restrict__ partial, int pstride, unsigned int *__restrict__ counter,
+                double *__restrict__ partial, unsigned int *__restrict__ counters,
                 double *__restrict__ h_out, const double *__restrict__ h_prev, double *__restrict__ alpha_out,
                 int j_alpha) {
-  __shared__ double sm[8];
+  __shared__ double sm[LZ_THREADS / 32][MD_COLS];
   __shared__ bool am_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = blockIdx.y * MD_COLS;
+  const int nc = min(MD_COLS, ncols - c0);
+  const unsigned nbx = gridDim.x;
+  const int32_t i = (blockIdx.x * LZ_THREADS + tid) * 2;
   double acc[MD_COLS];
 #pragma unroll
   for (int g = 0; g < MD_COLS; ++g) acc[g] = 0.0;
-  const int nc = min(MD_COLS, ncols - c0);
-  for (int32_t i = blockIdx.x * LZ_THREADS + threadIdx.x; i < n; i += gridDim.x * LZ_THREADS) {
-    const double wi = w[i];
+  if (i + 1 < n) {
+    const double2 w2 = *reinterpret_cast<const double2 *>(w + i);
+    double2 v[MD_COLS];
 #pragma unroll
     for (int g = 0; g < MD_COLS; ++g)
-      if (g < nc) acc[g] += V[(size_t)(c0 + g) * ld + i] * wi;
+      if (g < nc) v[g] = *reinterpret_cast<const double2 *>(V + (size_t)(c0 + g) * ld + i);
+#pragma unroll
+    for (int g = 0; g < MD_COLS; ++g)
+      if (g < nc) acc[g] = v[g].x * w2.x + v[g].y * w2.y;
+  } else if (i < n) {
+    const double w1 = w[i];
+#pragma unroll
+    for (int g = 0; g < MD_COLS; ++g)
+      if (g < nc) acc[g] = V[(size_t)(c0 + g) * ld + i] * w1;
   }
 #pragma unroll
   for (int g = 0; g < MD_COLS; ++g) {
-    const double s = block_sum_256(acc[g], sm);
-    if (threadIdx.x == 0 && g < nc) partial[(size_t)blockIdx.x * pstride + c0 + g] = s;
+    const double s = warp_sum(acc[g]);
+    if (lane == 0) sm[warp][g] = s;
+  }
+  __syncthreads();
+  if (tid < MD_COLS) {
+    double s = 0.0;
+#pragma unroll
+    for (int wi = 0; wi < LZ_THREADS / 32; ++wi) s += sm[wi][tid];
+    if (tid < nc) partial[(size_t)(c0 + tid) * nbx + blockIdx.x] = s;
   }
   __threadfence();
-  if (threadIdx.x == 0) {
-    const unsigned total = gridDim.x * gridDim.y;
-    am_last = (atomicInc(counter, total - 1) == total - 1);
-  }
+  __syncthreads();
+  if (tid == 0) am_last = (atomicInc(counters + blockIdx.y, nbx - 1) == nbx - 1);
   __syncthreads();
   if (!am_last) return;
   __threadfence();
-  for (int c = threadIdx.x; c < ncols; c += LZ_THREADS) {
+  if (warp < nc) {                        // one warp per column of this group
+    const int c = c0 + warp;
     double s = 0.0;
-    for (unsigned bx = 0; bx < gridDim.x; ++bx) s += __ldcg(&partial[(size_t)bx * pstride + c]);
-    h_out[c] = s;
-    if (alpha_out && c == j_alpha) alpha_out[j_alpha] = h_prev[c] + s;
+    for (unsigned bx = lane; bx < nbx; bx += 32) s += __ldcg(&partial[(size_t)c * nbx + bx]);
+    s = warp_sum(s);
+    if (lane == 0) {
+      h_out[c] = s;
+      if (alpha_out && c == j_alpha) alpha_out[j_alpha] = h_prev[c] + s;
+    }
   }
 }
 
-// w[i] -= sum_c V[c*ld+i] * h[c]; optionally norm2 = |w|^2, beta[j] = sqrt(norm2), scal[1] = 1/beta
+// w[i] -= sum_c V[c*ld+i] * h[c]; optionally norm2 = |w|^2, beta[j] = sqrt(norm2), scal[1] = 1/beta.
+// One row per thread; the column loop is unrolled 16-fold with all loads issued before the FMAs so a
+// thread keeps 16 independent 8-byte loads in flight (at n = 69 K that is 9 MB in flight chip-wide).
+constexpr int UP_UNROLL = 16;
 __global__ void __launch_bounds__(LZ_THREADS)
 update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__restrict__ w, int32_t n,
               const double *__restrict__ h, double *__restrict__ partial, unsigned int *__restrict__ counter,
@@ -111,13 +139,21 @@ update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__rest
   double nrm = 0.0;
   for (int32_t i = blockIdx.x * LZ_THREADS + threadIdx.x; i < n; i += gridDim.x * LZ_THREADS) {
     double s = w[i];
+    const double *vp = V + i;
     int c = 0;
+    for (; c + UP_UNROLL <= ncols; c += UP_UNROLL) {
+      double v[UP_UNROLL];
+#pragma unroll
+      for (int u = 0; u < UP_UNROLL; ++u) v[u] = vp[(size_t)(c + u) * ld];
+#pragma unroll
+      for (int u = 0; u < UP_UNROLL; ++u) s -= v[u] * hs[c + u];
+    }
     for (; c + 4 <= ncols; c += 4) {
-      const double v0 = V[(size_t)(c + 0) * ld + i], v1 = V[(size_t)(c + 1) * ld + i];
-      const double v2 = V[(size_t)(c + 2) * ld + i], v3 = V[(size_t)(c + 3) * ld + i];
+      const double v0 = vp[(size_t)(c + 0) * ld], v1 = vp[(size_t)(c + 1) * ld];
+      const double v2 = vp[(size_t)(c + 2) * ld], v3 = vp[(size_t)(c + 3) * ld];
       s -= v0 * hs[c + 0]; s -= v1 * hs[c + 1]; s -= v2 * hs[c + 2]; s -= v3 * hs[c + 3];
     }
-    for (; c < ncols; ++c) s -= V[(size_t)c * ld + i] * hs[c];
+    for (; c < ncols; ++c) s -= vp[(size_t)c * ld] * hs[c];
     w[i] = s;
     nrm += s * s;
   }
@@ -206,7 +242,6 @@ struct LzCtx {
   int m;
   size_t ld;
   int gx_md, gx_up;
-  int pstride;
 };
 
 void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out, const double *h_prev,
@@ -214,7 +249,7 @@ void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, doub
   auto &e = c.h->eig;
   dim3 grid((unsigned)c.gx_md, (unsigned)ceil_div(ncols, MD_COLS));
   c.h->prof.begin(KC_MULTIDOT, c.h->stream);
-  multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.n, e.partial.p, c.pstride, e.counters.p,
+  multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.n, e.partial.p, e.counters.p + 8,
                                                         h_out, h_prev, alpha_out, j);
   c.h->prof.end(c.h->stream);
   c.h->launches++;
@@ -260,19 +295,19 @@ void fiedler_solve(eigkl_handle *h) {
   LzCtx c;
   c.h = h; c.n = n; c.m = m;
   c.ld = ((size_t)n + 31) & ~(size_t)31;
-  c.gx_md = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, 2048), 4 * h->sm_count));
+  c.gx_md = (int)ceil_div(n, MD_ROWS);
   c.gx_up = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, LZ_THREADS), 8 * h->sm_count));
-  c.pstride = m + 1;
   e.n = n; e.ncv = m; e.ld = c.ld;
   for (int b = 0; b < 2; ++b) { e.V[b].ensure(c.ld * (size_t)(m + 1)); e.w[b].ensure(c.ld); }
-  e.partial.ensure((size_t)std::max(c.gx_md * c.pstride, c.gx_up) + 8);
+  e.partial.ensure((size_t)std::max<int64_t>((int64_t)c.gx_md * (m + 1), c.gx_up) + 8);
   e.hcoef.ensure(2 * (size_t)(m + 1));
   e.alpha.ensure((size_t)m); e.beta.ensure((size_t)m);
   e.scal.ensure(8);
-  e.counters.ensure(8);
+  const int n_counters = 8 + (m + 1 + MD_COLS - 1) / MD_COLS + 1;
+  e.counters.ensure((size_t)n_counters);
   e.Y.ensure((size_t)m * m);
   e.fiedler.ensure((size_t)n);
-  EIGKL_CUDA(cudaMemsetAsync(e.counters.p, 0, 8 * sizeof(unsigned int), st));
+  EIGKL_CUDA(cudaMemsetAsync(e.counters.p, 0, (size_t)n_counters * sizeof(unsigned int), st));
   const double one = 1.0;
   EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 2, &one, sizeof(double), cudaMemcpyHostToDevice, st));   // scal[2] = 1.0
 
