@@ -22,7 +22,7 @@ ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_FORMAT", -4: "E_CUDA", -5: "E
 SYMBOLS = [
     "eigkl_abi_version", "eigkl_nccl_unique_id", "eigkl_create", "eigkl_destroy", "eigkl_last_error",
     "eigkl_get_stats", "eigkl_synchronize", "eigkl_load_hgr", "eigkl_set_pins", "eigkl_get_sizes",
-    "eigkl_invalidate", "eigkl_get_stream",
+    "eigkl_invalidate", "eigkl_get_stream", "eigkl_row_partition",
     "eigkl_assemble_laplacian", "eigkl_fiedler", "eigkl_partition_from_fiedler", "eigkl_write_eig",
     "eigkl_assemble_kl_graph", "eigkl_set_partition", "eigkl_set_partition_ordered", "eigkl_load_eig",
     "eigkl_kl_run", "eigkl_write_trace", "eigkl_get_partition", "eigkl_spmv", "eigkl_dvalues", "eigkl_cut",
@@ -101,6 +101,7 @@ def load_library(path=LIB_PATH):
     L.eigkl_get_sizes.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_int64)]
     L.eigkl_invalidate.argtypes = [H]
     L.eigkl_get_stream.argtypes = [H, P(C.c_void_p)]
+    L.eigkl_row_partition.argtypes = [C.c_int32, C.c_int32, C.c_int32, P(C.c_int32), P(C.c_int32), P(C.c_int32)]
     L.eigkl_assemble_laplacian.argtypes = [H]
     L.eigkl_fiedler.argtypes = [H, P(C.c_double), P(C.c_double)]
     L.eigkl_partition_from_fiedler.argtypes = [H, P(C.c_double), P(C.c_uint8)]
@@ -128,6 +129,15 @@ def load_library(path=LIB_PATH):
 
 def _ptr(a, t):
     return a.ctypes.data_as(C.POINTER(t)) if a is not None else None
+
+
+def row_partition(n_rows, nranks, rank):
+    """(row_lo, row_hi, rows_padded) of the multi-rank row partition (host-only, no GPU needed)."""
+    lo, hi, pad = C.c_int32(), C.c_int32(), C.c_int32()
+    rc = load_library().eigkl_row_partition(n_rows, nranks, rank, C.byref(lo), C.byref(hi), C.byref(pad))
+    if rc != 0:
+        raise EigklError(rc, "eigkl_row_partition: bad arguments")
+    return lo.value, hi.value, pad.value
 
 
 def nccl_unique_id():

@@ -264,14 +264,15 @@ __global__ void lap_diag_kernel(const int32_t *__restrict__ rowptr, const int32_
   col[dpos] = v;
   val[dpos] = -s;
 }
-// blk_row[b] = first row r with rowptr[r] >= b*chunk  (b in [0, n_blocks]; blk_row[n_blocks] = n)
-__global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t n, int64_t chunk, int32_t n_blocks,
-                                  int32_t *__restrict__ blk_row) {
+// blk_row[b] = first row r in [row_lo, row_hi] with rowptr[r] >= rowptr[row_lo] + b*chunk
+// (b in [0, n_blocks]; blk_row[n_blocks] = row_hi)
+__global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t row_lo, int32_t row_hi, int64_t chunk,
+                                  int32_t n_blocks, int32_t *__restrict__ blk_row) {
   int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > n_blocks) return;
-  if (b == n_blocks) { blk_row[b] = n; return; }
-  const int64_t x = (int64_t)b * chunk;
-  int32_t lo = 0, hi = n;
+  if (b == n_blocks) { blk_row[b] = row_hi; return; }
+  const int64_t x = (int64_t)rowptr[row_lo] + (int64_t)b * chunk;
+  int32_t lo = row_lo, hi = row_hi;
   while (lo < hi) {
     int32_t mid = (lo + hi) >> 1;
     if ((int64_t)rowptr[mid] < x) lo = mid + 1; else hi = mid;
@@ -312,10 +313,19 @@ void assemble_laplacian(eigkl_handle *h) {
     h->launches += 2;
   }
   lap_diag_kernel<<<grid_for(n), TPB, 0, h->stream>>>(L.rowptr.p, ue.bstart.p, n, L.col.p, L.val.p);
-  const int64_t chunk = pick_chunk(h, L.nnz);
-  L.n_blocks = (int32_t)ceil_div(L.nnz, chunk);
+  // this rank's row slice (the matrix itself is assembled in full on every rank: ~1 ms, and it keeps
+  // the assembly free of collectives; SpMV and every vector are row-partitioned)
+  int32_t n_pad = 0;
+  row_partition(n, h->opts.nranks, h->opts.rank, &L.row_lo, &L.row_hi, &n_pad);
+  int32_t rp[2] = {0, 0};
+  EIGKL_CUDA(cudaMemcpyAsync(&rp[0], L.rowptr.p + L.row_lo, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EIGKL_CUDA(cudaMemcpyAsync(&rp[1], L.rowptr.p + L.row_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  const int64_t nnz_local = (int64_t)rp[1] - rp[0];
+  const int64_t chunk = pick_chunk(h, nnz_local);
+  L.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(nnz_local, chunk));
   L.blk_row.alloc((size_t)L.n_blocks + 1);
-  row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, n, chunk, L.n_blocks, L.blk_row.p);
+  row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, L.row_lo, L.row_hi, chunk, L.n_blocks, L.blk_row.p);
   h->launches += 2;
   EIGKL_CUDA(cudaGetLastError());
   L.valid = true;
@@ -427,7 +437,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   const int64_t chunk = pick_chunk(h, A.nnz);
   A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz, chunk));
   A.blk_row.alloc((size_t)A.n_blocks + 1);
-  row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, n, chunk, A.n_blocks, A.blk_row.p);
+  row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, 0, n, chunk, A.n_blocks, A.blk_row.p);
   h->launches++;
   EIGKL_CUDA(cudaGetLastError());
   A.valid = true;

@@ -213,6 +213,12 @@ int eigkl_invalidate(eigkl_handle *h) {
   });
 }
 
+int eigkl_row_partition(int32_t n_rows, int32_t nranks, int32_t rank, int32_t *row_lo, int32_t *row_hi, int32_t *rows_padded) {
+  if (n_rows <= 0 || nranks <= 0 || rank < 0 || rank >= nranks || !row_lo || !row_hi || !rows_padded) return EIGKL_E_ARG;
+  row_partition(n_rows, nranks, rank, row_lo, row_hi, rows_padded);
+  return EIGKL_OK;
+}
+
 int eigkl_get_stream(const eigkl_handle *h, void **stream) {
   if (!h || !stream) return EIGKL_E_ARG;
   *stream = (void *)h->stream;
@@ -367,10 +373,16 @@ int eigkl_spmv(eigkl_handle *h, const double *x, double *y) {
     EIGKL_REQUIRE(x && y && h->L.valid, EIGKL_E_ARG, "eigkl_spmv: Laplacian not assembled");
     EIGKL_CUDA(cudaSetDevice(h->device));
     const size_t n = (size_t)h->L.n;
-    DBuf<double> dx, dy; dx.alloc(n); dy.alloc(n);
+    int32_t lo, hi, n_pad;
+    row_partition(h->L.n, h->opts.nranks, h->opts.rank, &lo, &hi, &n_pad);
+    const size_t full = (size_t)n_pad * (size_t)h->opts.nranks;
+    DBuf<double> dx, dy, dg; dx.alloc(n); dy.alloc((size_t)n_pad); dg.alloc(full);
     EIGKL_CUDA(cudaMemcpyAsync(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
-    spmv_launch(h, dx.p, dy.p, nullptr, nullptr);
-    EIGKL_CUDA(cudaMemcpyAsync(y, dy.p, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EIGKL_CUDA(cudaMemsetAsync(dy.p, 0, (size_t)n_pad * sizeof(double), h->stream));
+    spmv_launch(h, dx.p, dy.p, nullptr, nullptr);             // this rank's rows
+    const double *src = dy.p;
+    if (h->opts.nranks > 1) { comm_allgather_f64(h, dy.p, dg.p, (size_t)n_pad); src = dg.p; }
+    EIGKL_CUDA(cudaMemcpyAsync(y, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     EIGKL_CUDA(cudaStreamSynchronize(h->stream));
     EIGKL_CUDA(cudaGetLastError());
   });

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstring>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
 #include <vector>
 #include "eigkl.h"
@@ -144,7 +145,9 @@ struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, dia
   int64_t nnz = 0;
   DBuf<int32_t> rowptr, col;
   DBuf<double> val;
-  // row blocks of the adaptive SpMV: block b owns rows [blk_row[b], blk_row[b+1])
+  // this rank's rows [row_lo, row_hi) (everything when nranks == 1) cut into row blocks of the
+  // adaptive SpMV: block b owns rows [blk_row[b], blk_row[b+1])
+  int32_t row_lo = 0, row_hi = 0;
   int32_t n_blocks = 0;
   DBuf<int32_t> blk_row;
   bool valid = false;
@@ -190,7 +193,8 @@ struct EigState {
   DBuf<double> scal;           // [0] norm^2, [1] 1/beta, ...
   DBuf<unsigned int> counters; // last-block-done counters
   DBuf<double> Y;              // ncv*ncv restart coefficients (column major, ld = ncv)
-  DBuf<double> fiedler;        // n : result vector
+  DBuf<double> xfull;          // nranks * n_pad : all-gathered SpMV input (multi-rank only)
+  DBuf<double> fiedler;        // n (nranks * n_pad when multi-rank) : result vector
   DBuf<uint8_t> side;          // n : partition from the Fiedler vector
   DBuf<unsigned long long> sortkey[2];
   DBuf<uint32_t> sortval[2];
@@ -285,5 +289,15 @@ void comm_allgather_f64(eigkl_handle *h, const double *send, double *recv, size_
 void comm_broadcast_bytes(eigkl_handle *h, void *buf, size_t bytes, int root);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// 1-D row partition of n rows over nranks ranks: equal blocks of n_pad rows (a multiple of 32, so that
+// one ncclAllGather of n_pad values per rank rebuilds a full vector in place: global row g lives at
+// index g of the gathered buffer); the last ranks may own fewer (or zero) real rows.
+inline void row_partition(int32_t n, int nranks, int rank, int32_t *lo, int32_t *hi, int32_t *n_pad) {
+  int64_t per = ceil_div(n, nranks);
+  per = ceil_div(per, 32) * 32;
+  const int64_t l = std::min<int64_t>(n, per * rank), hh = std::min<int64_t>(n, per * (rank + 1));
+  *lo = (int32_t)l; *hi = (int32_t)hh; *n_pad = (int32_t)per;
+}
 
 }  // namespace eigkl

@@ -61,13 +61,11 @@ __device__ __forceinline__ double block_sum_256(double v, double *sm /* 8 double
 // 16-byte load per column) and MD_COLS columns, so a step with j columns exposes n/2 * j/8 threads with
 // 9 independent loads each -- enough bytes in flight to cover the L2/HBM latency even at n = 12 K.
 // partial[c * nbx + bx]; the last CTA of a column group (ticket counter per group) folds that group's
-// partials, one warp per column, in a fixed order.  pass 2 additionally writes alpha[j] = h1[j] + h2[j].
+// partials, one warp per column, in a fixed order.
 constexpr int MD_ROWS = 2 * LZ_THREADS;
 __global__ void __launch_bounds__(LZ_THREADS)
 multidot_kernel(const double *__restrict__ V, size_t ld, int ncols, const double *__restrict__ w, int32_t n,
-                double *__restrict__ partial, unsigned int *__restrict__ counters,
-                double *__restrict__ h_out, const double *__restrict__ h_prev, double *__restrict__ alpha_out,
-                int j_alpha) {
+                double *__restrict__ partial, unsigned int *__restrict__ counters, double *__restrict__ h_out) {
   __shared__ double sm[LZ_THREADS / 32][MD_COLS];
   __shared__ bool am_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -116,10 +114,7 @@ multidot_kernel(const double *__restrict__ V, size_t ld, int ncols, const double
     double s = 0.0;
     for (unsigned bx = lane; bx < nbx; bx += 32) s += __ldcg(&partial[(size_t)c * nbx + bx]);
     s = warp_sum(s);
-    if (lane == 0) {
-      h_out[c] = s;
-      if (alpha_out && c == j_alpha) alpha_out[j_alpha] = h_prev[c] + s;
-    }
+    if (lane == 0) h_out[c] = s;
   }
 }
 
@@ -130,12 +125,15 @@ constexpr int UP_UNROLL = 16;
 __global__ void __launch_bounds__(LZ_THREADS)
 update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__restrict__ w, int32_t n,
               const double *__restrict__ h, double *__restrict__ partial, unsigned int *__restrict__ counter,
-              double *__restrict__ scal, double *__restrict__ beta_out, int j_beta, int want_norm) {
+              double *__restrict__ scal, double *__restrict__ beta_out, int j_beta, int want_norm, int finalize,
+              const double *__restrict__ h_prev, double *__restrict__ alpha_out) {
   extern __shared__ double hs[];            // ncols
   __shared__ double sm[8];
   __shared__ bool am_last;
   for (int c = threadIdx.x; c < ncols; c += LZ_THREADS) hs[c] = h[c];
   __syncthreads();
+  // pass 2: alpha_j = h1[j] + h2[j] (the diagonal entry of the projected matrix)
+  if (alpha_out && blockIdx.x == 0 && threadIdx.x == 0) alpha_out[j_beta] = h_prev[j_beta] + hs[j_beta];
   double nrm = 0.0;
   for (int32_t i = blockIdx.x * LZ_THREADS + threadIdx.x; i < n; i += gridDim.x * LZ_THREADS) {
     double s = w[i];
@@ -171,7 +169,18 @@ update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__rest
   s = block_sum_256(s, sm);
   if (threadIdx.x == 0) {
     scal[0] = s;
-    const double beta = sqrt(s);
+    if (finalize) {                         // single rank: beta here; multi-rank: after the all-reduce
+      const double beta = sqrt(s);
+      scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
+      if (beta_out) beta_out[j_beta] = beta;
+    }
+  }
+}
+
+// multi-rank: scal[0] holds the all-reduced |w|^2
+__global__ void beta_kernel(double *__restrict__ scal, double *__restrict__ beta_out, int j_beta) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const double beta = sqrt(scal[0]);
     scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
     if (beta_out) beta_out[j_beta] = beta;
   }
@@ -238,42 +247,79 @@ namespace {
 
 struct LzCtx {
   eigkl_handle *h;
-  int32_t n;
+  int32_t n;        // global rows
+  int32_t nl;       // rows owned by this rank
+  int32_t row_lo;
+  int R;            // ranks
   int m;
-  size_t ld;
+  size_t ld;        // leading dimension of the local basis slice (= n_pad)
   int gx_md, gx_up;
 };
 
-void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out, const double *h_prev,
-                     double *alpha_out, int j) {
+void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out) {
   auto &e = c.h->eig;
-  dim3 grid((unsigned)c.gx_md, (unsigned)ceil_div(ncols, MD_COLS));
-  c.h->prof.begin(KC_MULTIDOT, c.h->stream);
-  multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.n, e.partial.p, e.counters.p + 8,
-                                                        h_out, h_prev, alpha_out, j);
-  c.h->prof.end(c.h->stream);
-  c.h->launches++;
-  c.h->stats.bytes_multidot_total += c.h->prof.on ? ((double)ncols * c.n * 8.0 + (double)c.n * 8.0) : 0.0;
+  if (c.nl > 0) {
+    dim3 grid((unsigned)c.gx_md, (unsigned)ceil_div(ncols, MD_COLS));
+    c.h->prof.begin(KC_MULTIDOT, c.h->stream);
+    multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.nl, e.partial.p, e.counters.p + 8, h_out);
+    c.h->prof.end(c.h->stream);
+    c.h->launches++;
+    c.h->stats.bytes_multidot_total += c.h->prof.on ? ((double)ncols * c.nl * 8.0 + (double)c.nl * 8.0) : 0.0;
+  } else {
+    EIGKL_CUDA(cudaMemsetAsync(h_out, 0, (size_t)ncols * sizeof(double), c.h->stream));
+  }
+  if (c.R > 1) comm_allreduce_sum_f64(c.h, h_out, (size_t)ncols);      // C2: Lanczos dot products
 }
-void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double *hcoef, double *beta_out, int j, int want_norm) {
+void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double *hcoef, const double *h_prev,
+                   double *alpha_out, double *beta_out, int j, int want_norm) {
   auto &e = c.h->eig;
-  c.h->prof.begin(KC_UPDATE, c.h->stream);
-  update_kernel<<<(unsigned)c.gx_up, LZ_THREADS, (size_t)ncols * sizeof(double), c.h->stream>>>(
-      V, c.ld, ncols, w, c.n, hcoef, e.partial.p, e.counters.p + 1, e.scal.p, beta_out, j, want_norm);
-  c.h->prof.end(c.h->stream);
-  c.h->launches++;
-  c.h->stats.bytes_update_total += c.h->prof.on ? ((double)ncols * c.n * 8.0 + (double)c.n * 16.0) : 0.0;
+  if (c.nl > 0) {
+    c.h->prof.begin(KC_UPDATE, c.h->stream);
+    update_kernel<<<(unsigned)c.gx_up, LZ_THREADS, (size_t)ncols * sizeof(double), c.h->stream>>>(
+        V, c.ld, ncols, w, c.nl, hcoef, e.partial.p, e.counters.p + 1, e.scal.p, beta_out, j, want_norm, c.R == 1 ? 1 : 0,
+        h_prev, alpha_out);
+    c.h->prof.end(c.h->stream);
+    c.h->launches++;
+    c.h->stats.bytes_update_total += c.h->prof.on ? ((double)ncols * c.nl * 8.0 + (double)c.nl * 16.0) : 0.0;
+  } else if (want_norm) {
+    EIGKL_CUDA(cudaMemsetAsync(e.scal.p, 0, sizeof(double), c.h->stream));
+  }
+  if (c.R > 1 && want_norm) {
+    comm_allreduce_sum_f64(c.h, e.scal.p, 1);
+    beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, beta_out, j);
+    c.h->launches++;
+  }
+}
+void launch_norm(LzCtx &c, const double *w) {
+  auto &e = c.h->eig;
+  if (c.nl > 0) {
+    norm_kernel<<<(unsigned)c.gx_up, LZ_THREADS, 0, c.h->stream>>>(w, c.nl, e.partial.p, e.counters.p + 1, e.scal.p);
+    c.h->launches++;
+  } else {
+    EIGKL_CUDA(cudaMemsetAsync(e.scal.p, 0, sizeof(double), c.h->stream));
+  }
+  if (c.R > 1) {
+    comm_allreduce_sum_f64(c.h, e.scal.p, 1);
+    beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, nullptr, 0);
+    c.h->launches++;
+  }
 }
 
-// one Lanczos step j: x_unscaled (with *scale) -> V[:, j]; leaves unscaled v_{j+1} in w_out, 1/beta in scal[1]
-void lanczos_step(LzCtx &c, double *V, int j, const double *x_unscaled, const double *scale, bool store, double *w_out) {
+// one Lanczos step j: x_local (this rank's slice of the un-normalised v_j, with *scale = 1/|v_j|) -> V[:, j];
+// leaves the un-normalised v_{j+1} slice in w_out and 1/beta_j in scal[1]
+void lanczos_step(LzCtx &c, double *V, int j, const double *x_local, const double *scale, bool store, double *w_out) {
   auto &e = c.h->eig;
-  spmv_launch(c.h, x_unscaled, w_out, scale, store ? V + (size_t)j * c.ld : nullptr);
+  const double *x = x_local;
+  if (c.R > 1) {                                                      // C1: SpMV halo exchange
+    comm_allgather_f64(c.h, x_local, e.xfull.p, c.ld);
+    x = e.xfull.p;
+  }
+  spmv_launch(c.h, x, w_out, scale, store ? V + (size_t)j * c.ld : nullptr);
   double *h1 = e.hcoef.p, *h2 = e.hcoef.p + (c.m + 1);
-  launch_multidot(c, V, j + 1, w_out, h1, nullptr, nullptr, j);
-  launch_update(c, V, j + 1, w_out, h1, nullptr, j, 0);
-  launch_multidot(c, V, j + 1, w_out, h2, h1, e.alpha.p, j);
-  launch_update(c, V, j + 1, w_out, h2, e.beta.p, j, 1);
+  launch_multidot(c, V, j + 1, w_out, h1);
+  launch_update(c, V, j + 1, w_out, h1, nullptr, nullptr, nullptr, j, 0);
+  launch_multidot(c, V, j + 1, w_out, h2);
+  launch_update(c, V, j + 1, w_out, h2, h1, e.alpha.p, e.beta.p, j, 1);
 }
 
 }  // namespace
@@ -282,7 +328,6 @@ void fiedler_solve(eigkl_handle *h) {
   auto &L = h->L;
   auto &e = h->eig;
   EIGKL_REQUIRE(L.valid, EIGKL_E_ARG, "eigkl_fiedler: call eigkl_assemble_laplacian first");
-  EIGKL_REQUIRE(h->opts.nranks <= 1, EIGKL_E_ARG, "eigkl_fiedler: multi-rank solve not available in this build");
   const int32_t n = L.n;
   const int nev = 2;
   int m = h->opts.ncv > 0 ? h->opts.ncv : std::min(100, n / 2);        // cEIG.cpp:195
@@ -293,10 +338,14 @@ void fiedler_solve(eigkl_handle *h) {
   cudaStream_t st = h->stream;
 
   LzCtx c;
-  c.h = h; c.n = n; c.m = m;
-  c.ld = ((size_t)n + 31) & ~(size_t)31;
-  c.gx_md = (int)ceil_div(n, MD_ROWS);
-  c.gx_up = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(n, LZ_THREADS), 8 * h->sm_count));
+  c.h = h; c.n = n; c.m = m; c.R = h->opts.nranks;
+  int32_t lo, hi, n_pad;
+  row_partition(n, c.R, h->opts.rank, &lo, &hi, &n_pad);
+  EIGKL_REQUIRE(lo == L.row_lo && hi == L.row_hi, EIGKL_E_ARG, "row partition changed since assembly");
+  c.nl = hi - lo; c.row_lo = lo;
+  c.ld = (size_t)n_pad;
+  c.gx_md = (int)std::max<int64_t>(1, ceil_div(c.nl, MD_ROWS));
+  c.gx_up = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(c.nl, LZ_THREADS), 8 * h->sm_count));
   e.n = n; e.ncv = m; e.ld = c.ld;
   for (int b = 0; b < 2; ++b) { e.V[b].ensure(c.ld * (size_t)(m + 1)); e.w[b].ensure(c.ld); }
   e.partial.ensure((size_t)std::max<int64_t>((int64_t)c.gx_md * (m + 1), c.gx_up) + 8);
@@ -306,15 +355,20 @@ void fiedler_solve(eigkl_handle *h) {
   const int n_counters = 8 + (m + 1 + MD_COLS - 1) / MD_COLS + 1;
   e.counters.ensure((size_t)n_counters);
   e.Y.ensure((size_t)m * m);
-  e.fiedler.ensure((size_t)n);
+  e.fiedler.ensure(c.ld * (size_t)c.R);
+  if (c.R > 1) e.xfull.ensure(c.ld * (size_t)c.R);
   EIGKL_CUDA(cudaMemsetAsync(e.counters.p, 0, (size_t)n_counters * sizeof(unsigned int), st));
+  for (int b = 0; b < 2; ++b) EIGKL_CUDA(cudaMemsetAsync(e.w[b].p, 0, c.ld * sizeof(double), st));
   const double one = 1.0;
   EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 2, &one, sizeof(double), cudaMemcpyHostToDevice, st));   // scal[2] = 1.0
 
-  // start vector (Spectra: SimpleRandom residual, uniform in [-0.5, 0.5); ours is seeded splitmix64)
-  fill_random_kernel<<<(unsigned)ceil_div(n, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[0].p, n, h->opts.seed + 0x9E3779B97F4A7C15ull, 0);
-  norm_kernel<<<(unsigned)c.gx_up, LZ_THREADS, 0, st>>>(e.w[0].p, n, e.partial.p, e.counters.p + 1, e.scal.p);
-  h->launches += 2;
+  // start vector (Spectra: SimpleRandom residual, uniform in [-0.5, 0.5); ours is a seeded splitmix64 of the
+  // GLOBAL row id, so the vector does not depend on the number of ranks)
+  if (c.nl > 0) {
+    fill_random_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[0].p, c.nl, h->opts.seed + 0x9E3779B97F4A7C15ull, lo);
+    h->launches++;
+  }
+  launch_norm(c, e.w[0].p);
 
   std::vector<double> T((size_t)m * m, 0.0), Yh((size_t)m * m), theta(m), alpha(m), beta(m), Ycm;
   int k = 0, cur = 0, bank = 0, it = 0, nmv = 0;
@@ -334,8 +388,10 @@ void fiedler_solve(eigkl_handle *h) {
       ++nmv;
     }
     // v_m = w / beta_m into column m
-    scale_store_kernel<<<(unsigned)ceil_div(n, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[cur].p, e.scal.p + 1, V + (size_t)m * c.ld, n);
-    h->launches++;
+    if (c.nl > 0) {
+      scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[cur].p, e.scal.p + 1, V + (size_t)m * c.ld, c.nl);
+      h->launches++;
+    }
     EIGKL_CUDA(cudaMemcpyAsync(alpha.data(), e.alpha.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     EIGKL_CUDA(cudaMemcpyAsync(beta.data(), e.beta.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
     EIGKL_CUDA(cudaStreamSynchronize(st));
@@ -356,20 +412,20 @@ void fiedler_solve(eigkl_handle *h) {
     if (it == maxit - 1) { ++it; break; }
     int kk = h->opts.keep > 0 ? h->opts.keep : std::max(nev + nconv, m / 5);
     kk = std::max(nev, std::min(kk, m - 2));
-    // V_new[:, 0:kk] = V[:, 0:m] Y[:, 0:kk];  V_new[:, kk] = v_m
+    // V_new[:, 0:kk] = V[:, 0:m] Y[:, 0:kk];  V_new[:, kk] = v_m   (rank-local: no communication)
     Ycm.assign((size_t)m * kk, 0.0);
     for (int cc = 0; cc < kk; ++cc)
       for (int j = 0; j < m; ++j) Ycm[(size_t)cc * m + j] = Yh[(size_t)j * m + cc];
     EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), Ycm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
     double *Vn = e.V[bank ^ 1].p;
-    {
-      dim3 grid((unsigned)ceil_div(n, LZ_THREADS), (unsigned)ceil_div(kk, RS_COLS));
+    if (c.nl > 0) {
+      dim3 grid((unsigned)ceil_div(c.nl, LZ_THREADS), (unsigned)ceil_div(kk, RS_COLS));
       h->prof.begin(KC_RESTART, st);
-      restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(V, c.ld, m, e.Y.p, kk, Vn, c.ld, n);
+      restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(V, c.ld, m, e.Y.p, kk, Vn, c.ld, c.nl);
       h->prof.end(st);
       h->launches++;
     }
-    EIGKL_CUDA(cudaMemcpyAsync(Vn + (size_t)kk * c.ld, V + (size_t)m * c.ld, (size_t)n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    EIGKL_CUDA(cudaMemcpyAsync(Vn + (size_t)kk * c.ld, V + (size_t)m * c.ld, c.ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
     EIGKL_CUDA(cudaStreamSynchronize(st));    // Ycm is reused next cycle
     std::fill(T.begin(), T.end(), 0.0);
     for (int cc = 0; cc < kk; ++cc) {
@@ -387,11 +443,18 @@ void fiedler_solve(eigkl_handle *h) {
     Ycm.assign((size_t)m, 0.0);
     for (int j = 0; j < m; ++j) Ycm[j] = Yh[(size_t)j * m + 1];
     EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
-    dim3 grid((unsigned)ceil_div(n, LZ_THREADS), 1);
-    restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(e.V[bank].p, c.ld, m, e.Y.p, 1, e.w[0].p, c.ld, n);
-    norm_kernel<<<(unsigned)c.gx_up, LZ_THREADS, 0, st>>>(e.w[0].p, n, e.partial.p, e.counters.p + 1, e.scal.p);
-    scale_store_kernel<<<(unsigned)ceil_div(n, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[0].p, e.scal.p + 1, e.fiedler.p, n);
-    h->launches += 3;
+    double *slice = (c.R > 1) ? e.w[1].p : e.fiedler.p;
+    if (c.nl > 0) {
+      dim3 grid((unsigned)ceil_div(c.nl, LZ_THREADS), 1);
+      restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(e.V[bank].p, c.ld, m, e.Y.p, 1, e.w[0].p, c.ld, c.nl);
+      h->launches++;
+    }
+    launch_norm(c, e.w[0].p);
+    if (c.nl > 0) {
+      scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[0].p, e.scal.p + 1, slice, c.nl);
+      h->launches++;
+    }
+    if (c.R > 1) comm_allgather_f64(h, slice, e.fiedler.p, c.ld);     // every rank ends with the full vector
     EIGKL_CUDA(cudaStreamSynchronize(st));
   }
   EIGKL_CUDA(cudaGetLastError());

@@ -67,8 +67,9 @@ spmv_adaptive_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restri
   const double sc = scale ? __ldg(scale) : 1.0;
   const int32_t e0 = rowptr[r0], e1 = rowptr[r1];
   const int32_t span = e1 - e0, nrows = r1 - r0;
+  y -= row_offset;                       // rows are global ids; y and v_store are this rank's slices
   if (v_store) {
-    for (int32_t r = r0 + tid; r < r1; r += SPMV_THREADS) v_store[r] = __ldg(x + row_offset + r) * sc;
+    for (int32_t r = r0 + tid; r < r1; r += SPMV_THREADS) v_store[r - row_offset] = __ldg(x + r) * sc;
   }
   const int mean = span / nrows;
   const bool stream = WITH_STREAM && ((mode == 1) || (mode == 0 && mean < 4));
@@ -103,17 +104,19 @@ spmv_adaptive_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restri
   }
 }
 
+// x: full-length vector (global column ids); y / store_scaled: this rank's row slice
 void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scale_inv, double *store_scaled) {
   auto &L = h->L;
   EIGKL_REQUIRE(L.valid, EIGKL_E_ARG, "Laplacian not assembled");
+  if (L.row_hi <= L.row_lo) return;
   h->prof.begin(KC_SPMV, h->stream);
   const bool with_stream = h->spmv_mode == 1 || (h->spmv_mode == 0 && L.nnz < 6 * (int64_t)L.n);
   if (with_stream)
     spmv_adaptive_kernel<true><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, x, y, L.blk_row.p,
-                                                                                   scale_inv, store_scaled, 0, h->spmv_mode);
+                                                                                   scale_inv, store_scaled, L.row_lo, h->spmv_mode);
   else
     spmv_adaptive_kernel<false><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, x, y, L.blk_row.p,
-                                                                                    scale_inv, store_scaled, 0, h->spmv_mode);
+                                                                                    scale_inv, store_scaled, L.row_lo, h->spmv_mode);
   h->prof.end(h->stream);
   h->launches++;
 }

@@ -116,6 +116,11 @@ int  eigkl_get_sizes(const eigkl_handle *h, int32_t *n_nodes, int32_t *n_nets, i
 /* Drops everything derived from the pins (assembled matrices, Fiedler vector, partition) but keeps the
  * pins resident in HBM, so that the next eigkl_assemble_* call redoes the sort + segmented reduce.   */
 int  eigkl_invalidate(eigkl_handle *h);
+/* The 1-D row partition used when nranks > 1 (host-only, needs no GPU): rank owns rows [row_lo,row_hi)
+ * of the Laplacian and of every Lanczos vector; rows_padded (a multiple of 32) is the per-rank slot of
+ * the all-gathered vectors, so global row g sits at index g of a gathered buffer.                     */
+int  eigkl_row_partition(int32_t n_rows, int32_t nranks, int32_t rank, int32_t *row_lo, int32_t *row_hi,
+                         int32_t *rows_padded);
 /* The CUDA stream (cudaStream_t) every kernel of this handle is launched on, for callers that want to
  * record their own events around calls.                                                              */
 int  eigkl_get_stream(const eigkl_handle *h, void **stream);
