@@ -399,7 +399,7 @@ def main():
                 "dtype": "f64 (Lanczos) + f32 (KL, bit-exact with the reference)",
                 "data": ("real circuit %s.hgr (ISPD98)" % name) if not name.startswith("synth") else "synthetic (seeded circuit_generator restatement)",
                 "config": {"workload": name, "nodes": n_nodes, "nets": n_nets, "pins": int(len(pins)),
-                           "parallelism": ("Lanczos row-partitioned over %d ranks (NCCL all-gather + all-reduce), assembly and KL replicated" % world) if world > 1 else "1 GPU",
+                           "parallelism": ("Lanczos row-partitioned over %d ranks (NCCL halo all-gather + dot all-reduces); KL D-values/arg-max partitioned by node range with one NCCL max all-reduce per swap; O(1 ms) assembly replicated" % world) if world > 1 else "1 GPU",
                            "l2": "working set < L2: every step re-assembles and re-solves from the resident pins; inputs are not flushed between steps",
                            "ncv": st["ncv"], "matvecs_per_pass": st["matvecs"], "restarts": st["restarts"], "kl_swaps": st["kl_swaps"],
                            "kl_cluster": st["kl_cluster"]},

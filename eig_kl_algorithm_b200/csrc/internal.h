@@ -177,6 +177,7 @@ struct KlState {
   DBuf<float> t_cut, t_gain;
   DBuf<int32_t> t_n1, t_n2;
   DBuf<int64_t> ctrl;          // [0] swaps, [1] status
+  DBuf<int64_t> mctrl;         // multi-rank loop state (KlCtrl, 32 bytes)
   int64_t swaps = 0;
   int64_t cap = 0;
 };
@@ -192,6 +193,7 @@ struct EigState {
   DBuf<double> alpha, beta;    // ncv each
   DBuf<double> scal;           // [0] norm^2, [1] 1/beta, ...
   DBuf<unsigned int> counters; // last-block-done counters
+  DBuf<int> flag;              // [0] = 1: second Gram-Schmidt pass of the current step is skipped
   DBuf<double> Y;              // ncv*ncv restart coefficients (column major, ld = ncv)
   DBuf<double> xfull;          // nranks * n_pad : all-gathered SpMV input (multi-rank only)
   DBuf<double> fiedler;        // n (nranks * n_pad when multi-rank) : result vector

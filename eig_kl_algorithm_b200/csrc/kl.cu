@@ -30,6 +30,7 @@
 #include <cooperative_groups.h>
 #include <algorithm>
 #include <cmath>
+#include <cstddef>
 
 namespace cg = cooperative_groups;
 
@@ -347,14 +348,15 @@ float kl_cut0(eigkl_handle *h) {
 // ---------------------------------------------------------------------------------------------------
 // tile keys
 // ---------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void tile_scan(const uint8_t *state, const float *val, const uint32_t *__restrict__ rank, int32_t n,
-                                          int32_t tile, int lane, unsigned long long &k0, unsigned long long &k1) {
+// [lo, hi): the nodes this rank owns (everything on one GPU); other nodes of the tile are ignored
+__device__ __forceinline__ void tile_scan(const uint8_t *state, const float *val, const uint32_t *__restrict__ rank, int32_t lo,
+                                          int32_t hi, int32_t tile, int lane, unsigned long long &k0, unsigned long long &k1) {
   k0 = 0ull; k1 = 0ull;
   const int32_t base = tile * KL_TILE;
 #pragma unroll
   for (int r = 0; r < KL_TILE / 32; ++r) {
     const int32_t u = base + r * 32 + lane;
-    if (u < n) {
+    if (u >= lo && u < hi) {
       const unsigned s = __ldcg(state + u);
       if (!(s & ST_LOCK)) {
         const float v = __ldcg(val + u);
@@ -368,12 +370,13 @@ __device__ __forceinline__ void tile_scan(const uint8_t *state, const float *val
   k1 = warp_max_u64(k1);
 }
 __global__ void tile_init_kernel(const uint8_t *__restrict__ state, const float *__restrict__ val, const uint32_t *__restrict__ rank,
-                                 int32_t n, int32_t n_tiles, unsigned long long *__restrict__ tile_key, uint32_t *__restrict__ tile_stamp) {
+                                 int32_t own_lo, int32_t own_hi, int32_t n_tiles, unsigned long long *__restrict__ tile_key,
+                                 uint32_t *__restrict__ tile_stamp) {
   const int lane = threadIdx.x & 31;
   const int32_t tile = (int32_t)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   if (tile >= n_tiles) return;
   unsigned long long k0, k1;
-  tile_scan(state, val, rank, n, tile, lane, k0, k1);
+  tile_scan(state, val, rank, own_lo, own_hi, tile, lane, k0, k1);
   if (lane == 0) { tile_key[2 * tile] = k0; tile_key[2 * tile + 1] = k1; tile_stamp[tile] = 0u; }
 }
 
@@ -401,8 +404,44 @@ struct KlLoopParams {
   float cut0;
   uint32_t term_limit;
   int64_t n0, n1;
+  int32_t own_lo, own_hi;           // nodes whose D-values / tile keys this rank maintains
+  struct KlCtrl *mctrl;             // multi-rank: loop state carried between the per-swap launches
 };
 
+struct KlCtrl {                     // multi-rank loop state (device memory)
+  float cut;
+  uint32_t term, iter;
+  int32_t done;
+  long long rem0, rem1;
+};
+
+// multi-rank S1: best pair over THIS rank's tiles -> exch[0..1] (then ncclAllReduce(max) across ranks: C3)
+__global__ void __launch_bounds__(KL_LOOP_THREADS)
+kl_select_kernel(const unsigned long long *__restrict__ tile_key, int32_t tile_lo, int32_t tile_hi,
+                 unsigned long long *__restrict__ exch, const KlCtrl *__restrict__ mctrl) {
+  __shared__ unsigned long long red0[32], red1[32];
+  if (mctrl->done) return;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned long long k0 = 0ull, k1 = 0ull;
+  for (int32_t t = tile_lo + tid; t < tile_hi; t += KL_LOOP_THREADS) {
+    const unsigned long long a0 = __ldcg(tile_key + 2 * (size_t)t), a1 = __ldcg(tile_key + 2 * (size_t)t + 1);
+    k0 = a0 > k0 ? a0 : k0;
+    k1 = a1 > k1 ? a1 : k1;
+  }
+  k0 = warp_max_u64(k0);
+  k1 = warp_max_u64(k1);
+  if (lane == 0) { red0[warp] = k0; red1[warp] = k1; }
+  __syncthreads();
+  if (warp == 0) {
+    k0 = warp_max_u64(red0[lane]);
+    k1 = warp_max_u64(red1[lane]);
+    if (lane == 0) { exch[0] = k0; exch[1] = k1; }
+  }
+}
+
+// MULTI = false: the whole pass in one launch.  MULTI = true: ONE swap per launch -- the pair comes from
+// exch[] (all-reduced over the ranks), the loop state from *p.mctrl, and only owned nodes are updated.
+template <bool MULTI>
 __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoopParams p) {
   cg::cluster_group cluster = cg::this_cluster();
   const unsigned nc = cluster.num_blocks();
@@ -422,14 +461,22 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
   __shared__ int sh_done;
   __shared__ long long sh_rem0, sh_rem1;
   if (tid == 0) {
-    sh_cut = p.cut0; sh_term = 0; sh_iter = 0; sh_done = 0; sh_rem0 = p.n0; sh_rem1 = p.n1;
-    if (p.n0 <= 0 || p.n1 <= 0) sh_done = 1;
+    if (MULTI) {
+      sh_cut = p.mctrl->cut; sh_term = p.mctrl->term; sh_iter = p.mctrl->iter; sh_done = p.mctrl->done;
+      sh_rem0 = p.mctrl->rem0; sh_rem1 = p.mctrl->rem1;
+    } else {
+      sh_cut = p.cut0; sh_term = 0; sh_iter = 0; sh_done = 0; sh_rem0 = p.n0; sh_rem1 = p.n1;
+      if (p.n0 <= 0 || p.n1 <= 0) sh_done = 1;
+    }
   }
   __syncthreads();
 
   while (!sh_done) {
     // ---- S1: best pair over the cached tile keys ------------------------------------------------
     unsigned long long k0 = 0ull, k1 = 0ull;
+    if (MULTI) {
+      if (tid == 0) { sh_best[0] = __ldcg(exch); sh_best[1] = __ldcg(exch + 1); }
+    } else {
     for (uint32_t t = gtid; t < (uint32_t)p.n_tiles; t += total_threads) {
       const unsigned long long a0 = __ldcg(p.tile_key + 2 * (size_t)t), a1 = __ldcg(p.tile_key + 2 * (size_t)t + 1);
       k0 = a0 > k0 ? a0 : k0;
@@ -457,6 +504,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
         if (lane == 0) { sh_best[0] = k0; sh_best[1] = k1; }
       }
     }
+    }   // !MULTI
     if (tid == 0) sh_w = 0.0f;
     __syncthreads();
     const unsigned long long b0 = sh_best[0], b1 = sh_best[1];
@@ -494,6 +542,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
     const int32_t da = ahi - alo, items = da + (bhi - blo);
     for (int32_t it = gwarp; it < items; it += total_warps) {
       const int32_t v = __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
+      if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;       // another rank owns this D-value
       const float nv = warp_row_value(p.col, p.w, p.state, __ldg(p.rowptr + v), __ldg(p.rowptr + v + 1), a, b, lane);
       if (lane == 0) __stcg(p.val + v, nv);
     }
@@ -505,19 +554,27 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
       if (it < da) v = __ldg(p.col + alo + it);
       else if (it < items) v = __ldg(p.col + blo + (it - da));
       else v = (it == items) ? a : b;
+      if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;
       const int32_t tile = v / KL_TILE;
       unsigned claimed = 0;
       if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
       claimed = __shfl_sync(FULL_MASK, claimed, 0);
       if (claimed) {
         unsigned long long t0, t1;
-        tile_scan(p.state, p.val, p.rank, p.n, tile, lane, t0, t1);
+        tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, tile, lane, t0, t1);
         if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
       }
     }
     cluster.sync();
+    if (MULTI) break;                                  // one swap per launch
   }
-  if (cr == 0 && tid == 0) { p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1; }
+  if (cr == 0 && tid == 0) {
+    if (MULTI) {
+      p.mctrl->cut = sh_cut; p.mctrl->term = sh_term; p.mctrl->iter = sh_iter; p.mctrl->done = sh_done;
+      p.mctrl->rem0 = sh_rem0; p.mctrl->rem1 = sh_rem1;
+    }
+    p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1;
+  }
 }
 
 void kl_run(eigkl_handle *h) {
@@ -535,7 +592,10 @@ void kl_run(eigkl_handle *h) {
   const float cut0 = kl_cut0(h);                                     // cKL.cpp:306
   kl_dvalues(h);                                                     // cKL.cpp:318-321
   const int32_t n_tiles = (int32_t)ceil_div(n, KL_TILE);
-  tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, n, n_tiles, k.tile_key.p, k.tile_stamp.p);
+  const int R = h->opts.nranks;
+  int32_t own_lo = 0, own_hi = n, own_pad = 0;
+  if (R > 1) row_partition(n, R, h->opts.rank, &own_lo, &own_hi, &own_pad);
+  tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, own_lo, own_hi, n_tiles, k.tile_key.p, k.tile_stamp.p);
   h->launches++;
   const float zero = 0.0f; const int32_t neg = -1;
   EIGKL_CUDA(cudaMemcpyAsync(k.t_cut.p, &cut0, sizeof(float), cudaMemcpyHostToDevice, st));
@@ -557,11 +617,16 @@ void kl_run(eigkl_handle *h) {
   p.cut0 = cut0;
   p.term_limit = (uint32_t)std::log2((double)n) + 5;                 // cKL.cpp:303
   p.n0 = k.n0; p.n1 = k.n1;
+  p.own_lo = own_lo; p.own_hi = own_hi;
+  p.mctrl = nullptr;
 
   int nc = h->opts.kl_cluster;
   if (nc <= 0) nc = (n <= 4096) ? 1 : 8;
   EIGKL_REQUIRE(nc == 1 || nc == 2 || nc == 4 || nc == 8 || nc == 16, EIGKL_E_ARG, "kl_cluster must be 1, 2, 4, 8 or 16");
-  if (nc > 8) EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  if (nc > 8) {
+    EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_kernel<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)nc);
   cfg.blockDim = dim3(KL_LOOP_THREADS);
@@ -572,8 +637,34 @@ void kl_run(eigkl_handle *h) {
   attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   h->timer.start(st);
-  EIGKL_CUDA(cudaLaunchKernelEx(&cfg, kl_loop_kernel, p));
-  h->launches++;
+  if (R == 1) {
+    EIGKL_CUDA(cudaLaunchKernelEx(&cfg, kl_loop_kernel<false>, p));
+    h->launches++;
+  } else {
+    // multi-rank: D-values and tile keys are partitioned by node range, the side
+    // bytes are replicated; per swap: local arg-max -> ncclAllReduce(max, 2 x uint64 packed keys) ->
+    // every rank applies the swap to its replica and recomputes the D-values it owns.  Swaps are
+    // issued in batches; the done flag is read back once per batch.
+    k.mctrl.ensure(8);
+    KlCtrl init{cut0, 0u, 0u, (k.n0 <= 0 || k.n1 <= 0) ? 1 : 0, (long long)k.n0, (long long)k.n1};
+    EIGKL_CUDA(cudaMemcpyAsync(k.mctrl.p, &init, sizeof(init), cudaMemcpyHostToDevice, st));
+    p.mctrl = reinterpret_cast<KlCtrl *>(k.mctrl.p);
+    unsigned long long *exch = k.tile_key.p + 2 * (size_t)n_tiles;
+    const int32_t tile_lo = own_lo / KL_TILE, tile_hi = (int32_t)ceil_div(own_hi, KL_TILE);
+    const int batch = 64;
+    const int64_t max_swaps = std::min(k.n0, k.n1);
+    int32_t done = init.done;
+    for (int64_t issued = 0; !done && issued < max_swaps + batch; issued += batch) {
+      for (int i = 0; i < batch; ++i) {
+        kl_select_kernel<<<1, KL_LOOP_THREADS, 0, st>>>(k.tile_key.p, tile_lo, own_hi > own_lo ? tile_hi : tile_lo, exch, p.mctrl);
+        comm_allreduce_max_u64(h, exch, 2);
+        EIGKL_CUDA(cudaLaunchKernelEx(&cfg, kl_loop_kernel<true>, p));
+        h->launches += 2;
+      }
+      EIGKL_CUDA(cudaMemcpyAsync(&done, reinterpret_cast<char *>(k.mctrl.p) + offsetof(KlCtrl, done), sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      EIGKL_CUDA(cudaStreamSynchronize(st));
+    }
+  }
   h->timer.stop(st);
   int64_t ctrl[2] = {0, 0};
   EIGKL_CUDA(cudaMemcpyAsync(ctrl, k.ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, st));

@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cfloat>
+#include <cstdlib>
 
 namespace eigkl {
 
@@ -65,9 +66,11 @@ __device__ __forceinline__ double block_sum_256(double v, double *sm /* 8 double
 constexpr int MD_ROWS = 2 * LZ_THREADS;
 __global__ void __launch_bounds__(LZ_THREADS)
 multidot_kernel(const double *__restrict__ V, size_t ld, int ncols, const double *__restrict__ w, int32_t n,
-                double *__restrict__ partial, unsigned int *__restrict__ counters, double *__restrict__ h_out) {
+                double *__restrict__ partial, unsigned int *__restrict__ counters, double *__restrict__ h_out,
+                const int *__restrict__ skip_flag) {
   __shared__ double sm[LZ_THREADS / 32][MD_COLS];
   __shared__ bool am_last;
+  if (skip_flag && *skip_flag) return;      // second Gram-Schmidt pass not needed (see update_kernel)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = blockIdx.y * MD_COLS;
   const int nc = min(MD_COLS, ncols - c0);
@@ -118,24 +121,36 @@ multidot_kernel(const double *__restrict__ V, size_t ld, int ncols, const double
   }
 }
 
-// w[i] -= sum_c V[c*ld+i] * h[c]; optionally norm2 = |w|^2, beta[j] = sqrt(norm2), scal[1] = 1/beta.
-// One row per thread; the column loop is unrolled 16-fold with all loads issued before the FMAs so a
+// w[i] -= sum_c V[c*ld+i] * h[c], plus the reductions that finish a Gram-Schmidt pass.
+//
+// One row per thread; the column loop is unrolled 16-fold with all loads issued before the FMAs, so a
 // thread keeps 16 independent 8-byte loads in flight (at n = 69 K that is 9 MB in flight chip-wide).
+// (A variant with 8 column slices per row and one load round was measured 25% slower on ibm10: 111
+// registers, 2 CTAs/SM, 4 waves.)
+//
+// pass 1 (DGKS test, the criterion ARPACK/Spectra-class solvers use): with V orthonormal,
+//   |w_before|^2 = |w_after|^2 + |h|^2.  If |w_after| > eta * |w_before| the first pass lost at most
+//   eps/eta of orthogonality and the second pass is skipped: flag = 1, beta_j = |w_after|, alpha_j = h[j].
+//   Otherwise flag = 0 and pass 2 (multidot + update) runs and finalises alpha_j = h1[j] + h2[j], beta_j.
+// pass 2 kernels return at once when flag == 1.
+// single == 0 (multi-rank): the kernel only leaves its local |w|^2 in scal[0]; the decision / beta are
+// taken by decide_kernel / beta_kernel after the all-reduce.
+constexpr int UP_ROWS = LZ_THREADS;       // rows per CTA
 constexpr int UP_UNROLL = 16;
 __global__ void __launch_bounds__(LZ_THREADS)
 update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__restrict__ w, int32_t n,
               const double *__restrict__ h, double *__restrict__ partial, unsigned int *__restrict__ counter,
-              double *__restrict__ scal, double *__restrict__ beta_out, int j_beta, int want_norm, int finalize,
-              const double *__restrict__ h_prev, double *__restrict__ alpha_out) {
+              double *__restrict__ scal, double *__restrict__ beta_out, double *__restrict__ alpha_out,
+              const double *__restrict__ h_prev, int j, int pass, int single, double eta2, int *__restrict__ flag) {
   extern __shared__ double hs[];            // ncols
   __shared__ double sm[8];
   __shared__ bool am_last;
-  for (int c = threadIdx.x; c < ncols; c += LZ_THREADS) hs[c] = h[c];
+  if (pass == 2 && *flag) return;           // second pass not needed (uniform for the whole grid)
+  const int tid = threadIdx.x;
+  for (int c = tid; c < ncols; c += LZ_THREADS) hs[c] = h[c];
   __syncthreads();
-  // pass 2: alpha_j = h1[j] + h2[j] (the diagonal entry of the projected matrix)
-  if (alpha_out && blockIdx.x == 0 && threadIdx.x == 0) alpha_out[j_beta] = h_prev[j_beta] + hs[j_beta];
   double nrm = 0.0;
-  for (int32_t i = blockIdx.x * LZ_THREADS + threadIdx.x; i < n; i += gridDim.x * LZ_THREADS) {
+  for (int32_t i = blockIdx.x * LZ_THREADS + tid; i < n; i += gridDim.x * LZ_THREADS) {
     double s = w[i];
     const double *vp = V + i;
     int c = 0;
@@ -155,34 +170,64 @@ update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__rest
     w[i] = s;
     nrm += s * s;
   }
-  if (!want_norm) return;
   const double bs = block_sum_256(nrm, sm);
-  if (threadIdx.x == 0) partial[blockIdx.x] = bs;
+  if (tid == 0) partial[blockIdx.x] = bs;
   __threadfence();
-  if (threadIdx.x == 0) am_last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
+  if (tid == 0) am_last = (atomicInc(counter, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
   if (!am_last) return;
   __threadfence();
   double s = 0.0;
-  // fixed-order fold: thread t sums partials t, t+256, ... then a block reduction
-  for (unsigned b = threadIdx.x; b < gridDim.x; b += LZ_THREADS) s += __ldcg(&partial[b]);
+  for (unsigned b = tid; b < gridDim.x; b += LZ_THREADS) s += __ldcg(&partial[b]);   // fixed-order fold
   s = block_sum_256(s, sm);
-  if (threadIdx.x == 0) {
+  double hh = 0.0;
+  if (pass == 1) {
+    for (int c = tid; c < ncols; c += LZ_THREADS) hh += hs[c] * hs[c];
+    hh = block_sum_256(hh, sm);
+  }
+  if (tid == 0) {
     scal[0] = s;
-    if (finalize) {                         // single rank: beta here; multi-rank: after the all-reduce
-      const double beta = sqrt(s);
-      scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
-      if (beta_out) beta_out[j_beta] = beta;
+    if (single) {
+      const bool skip = (pass == 1) && (s > eta2 * (s + hh));
+      if (pass == 1) *flag = skip ? 1 : 0;
+      if (pass == 2 || skip) {
+        const double beta = sqrt(s);
+        scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
+        beta_out[j] = beta;
+        alpha_out[j] = (pass == 2) ? h_prev[j] + hs[j] : hs[j];
+      }
     }
   }
 }
 
-// multi-rank: scal[0] holds the all-reduced |w|^2
-__global__ void beta_kernel(double *__restrict__ scal, double *__restrict__ beta_out, int j_beta) {
+// multi-rank, after the all-reduce of |w|^2 (scal[0]): the pass-1 decision ...
+__global__ void decide_kernel(double *__restrict__ scal, const double *__restrict__ h1, int ncols, double eta2,
+                              int *__restrict__ flag, double *__restrict__ beta_out, double *__restrict__ alpha_out, int j) {
+  __shared__ double sm[8];
+  double hh = 0.0;
+  for (int c = threadIdx.x; c < ncols; c += LZ_THREADS) hh += h1[c] * h1[c];
+  hh = block_sum_256(hh, sm);
+  if (threadIdx.x == 0) {
+    const double s = scal[0];
+    const bool skip = s > eta2 * (s + hh);
+    *flag = skip ? 1 : 0;
+    if (skip) {
+      const double beta = sqrt(s);
+      scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
+      beta_out[j] = beta;
+      alpha_out[j] = h1[j];
+    }
+  }
+}
+// ... and the pass-2 finalisation (also used for the norm of the start / Ritz vector: flag == nullptr)
+__global__ void beta_kernel(double *__restrict__ scal, double *__restrict__ beta_out, double *__restrict__ alpha_out,
+                            const double *__restrict__ h1, const double *__restrict__ h2, int j, const int *__restrict__ flag) {
   if (threadIdx.x == 0 && blockIdx.x == 0) {
+    if (flag && *flag) return;
     const double beta = sqrt(scal[0]);
     scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
-    if (beta_out) beta_out[j_beta] = beta;
+    if (beta_out) beta_out[j] = beta;
+    if (alpha_out) alpha_out[j] = h1[j] + h2[j];
   }
 }
 
@@ -254,14 +299,16 @@ struct LzCtx {
   int m;
   size_t ld;        // leading dimension of the local basis slice (= n_pad)
   int gx_md, gx_up;
+  double eta2;      // DGKS threshold squared
 };
 
-void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out) {
+void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out, int pass) {
   auto &e = c.h->eig;
   if (c.nl > 0) {
     dim3 grid((unsigned)c.gx_md, (unsigned)ceil_div(ncols, MD_COLS));
     c.h->prof.begin(KC_MULTIDOT, c.h->stream);
-    multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.nl, e.partial.p, e.counters.p + 8, h_out);
+    multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.nl, e.partial.p, e.counters.p + 8, h_out,
+                                                        pass == 2 ? e.flag.p : nullptr);
     c.h->prof.end(c.h->stream);
     c.h->launches++;
     c.h->stats.bytes_multidot_total += c.h->prof.on ? ((double)ncols * c.nl * 8.0 + (double)c.nl * 8.0) : 0.0;
@@ -270,23 +317,24 @@ void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, doub
   }
   if (c.R > 1) comm_allreduce_sum_f64(c.h, h_out, (size_t)ncols);      // C2: Lanczos dot products
 }
-void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double *hcoef, const double *h_prev,
-                   double *alpha_out, double *beta_out, int j, int want_norm) {
+void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double *hcoef, const double *h_prev, int j, int pass) {
   auto &e = c.h->eig;
+  const int single = c.R == 1 ? 1 : 0;
   if (c.nl > 0) {
     c.h->prof.begin(KC_UPDATE, c.h->stream);
     update_kernel<<<(unsigned)c.gx_up, LZ_THREADS, (size_t)ncols * sizeof(double), c.h->stream>>>(
-        V, c.ld, ncols, w, c.nl, hcoef, e.partial.p, e.counters.p + 1, e.scal.p, beta_out, j, want_norm, c.R == 1 ? 1 : 0,
-        h_prev, alpha_out);
+        V, c.ld, ncols, w, c.nl, hcoef, e.partial.p, e.counters.p + 1, e.scal.p, e.beta.p, e.alpha.p, h_prev, j, pass, single,
+        c.eta2, e.flag.p);
     c.h->prof.end(c.h->stream);
     c.h->launches++;
     c.h->stats.bytes_update_total += c.h->prof.on ? ((double)ncols * c.nl * 8.0 + (double)c.nl * 16.0) : 0.0;
-  } else if (want_norm) {
+  } else {
     EIGKL_CUDA(cudaMemsetAsync(e.scal.p, 0, sizeof(double), c.h->stream));
   }
-  if (c.R > 1 && want_norm) {
+  if (!single) {
     comm_allreduce_sum_f64(c.h, e.scal.p, 1);
-    beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, beta_out, j);
+    if (pass == 1) decide_kernel<<<1, LZ_THREADS, 0, c.h->stream>>>(e.scal.p, hcoef, ncols, c.eta2, e.flag.p, e.beta.p, e.alpha.p, j);
+    else beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, e.beta.p, e.alpha.p, h_prev, hcoef, j, e.flag.p);
     c.h->launches++;
   }
 }
@@ -300,7 +348,7 @@ void launch_norm(LzCtx &c, const double *w) {
   }
   if (c.R > 1) {
     comm_allreduce_sum_f64(c.h, e.scal.p, 1);
-    beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, nullptr, 0);
+    beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
     c.h->launches++;
   }
 }
@@ -316,10 +364,10 @@ void lanczos_step(LzCtx &c, double *V, int j, const double *x_local, const doubl
   }
   spmv_launch(c.h, x, w_out, scale, store ? V + (size_t)j * c.ld : nullptr);
   double *h1 = e.hcoef.p, *h2 = e.hcoef.p + (c.m + 1);
-  launch_multidot(c, V, j + 1, w_out, h1);
-  launch_update(c, V, j + 1, w_out, h1, nullptr, nullptr, nullptr, j, 0);
-  launch_multidot(c, V, j + 1, w_out, h2);
-  launch_update(c, V, j + 1, w_out, h2, h1, e.alpha.p, e.beta.p, j, 1);
+  launch_multidot(c, V, j + 1, w_out, h1, 1);
+  launch_update(c, V, j + 1, w_out, h1, nullptr, j, 1);      // sets flag = 1 when the second pass can be skipped
+  launch_multidot(c, V, j + 1, w_out, h2, 2);
+  launch_update(c, V, j + 1, w_out, h2, h1, j, 2);
 }
 
 }  // namespace
@@ -345,13 +393,22 @@ void fiedler_solve(eigkl_handle *h) {
   c.nl = hi - lo; c.row_lo = lo;
   c.ld = (size_t)n_pad;
   c.gx_md = (int)std::max<int64_t>(1, ceil_div(c.nl, MD_ROWS));
-  c.gx_up = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(c.nl, LZ_THREADS), 8 * h->sm_count));
+  c.gx_up = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(c.nl, UP_ROWS), 8 * h->sm_count));
+  {
+    // second Gram-Schmidt pass only when |w_after| <= eta |w_before| (eta = 1/sqrt(2) is the classical
+    // "twice is enough" bound; EIGKL_DGKS_ETA overrides, 1.0 forces both passes every step)
+    double eta = 0.70710678118654752;
+    if (const char *ev = getenv("EIGKL_DGKS_ETA")) eta = atof(ev);
+    c.eta2 = eta * eta;
+  }
   e.n = n; e.ncv = m; e.ld = c.ld;
   for (int b = 0; b < 2; ++b) { e.V[b].ensure(c.ld * (size_t)(m + 1)); e.w[b].ensure(c.ld); }
   e.partial.ensure((size_t)std::max<int64_t>((int64_t)c.gx_md * (m + 1), c.gx_up) + 8);
   e.hcoef.ensure(2 * (size_t)(m + 1));
   e.alpha.ensure((size_t)m); e.beta.ensure((size_t)m);
   e.scal.ensure(8);
+  e.flag.ensure(2);
+  EIGKL_CUDA(cudaMemsetAsync(e.flag.p, 0, 2 * sizeof(int), st));
   const int n_counters = 8 + (m + 1 + MD_COLS - 1) / MD_COLS + 1;
   e.counters.ensure((size_t)n_counters);
   e.Y.ensure((size_t)m * m);

@@ -48,9 +48,18 @@ if rank == 0:
         "swaps": (tr["swaps"], tr1["swaps"]),
     }
     ok = checks["spmv_equal"] and checks["lambda_rel"] < 1e-9 and sine < 1e-7
-    if np.array_equal(side, side1):
-        ok = ok and np.array_equal(tr["node1"], tr1["node1"]) and np.array_equal(tr["cut"], tr1["cut"])
-    print("MULTI", world, "lambda2", lam, "matvecs", st["matvecs"], "fiedler_ms %.2f" % st["ms_fiedler"], checks, "OK" if ok else "FAIL", flush=True)
+    # KL across ranks (NCCL arg-max exchange) must reproduce the single-GPU pass bit for bit from the same partition
+    with api.Handle(device=local) as h2:
+        h2.load_hgr(path)
+        h2.assemble_kl_graph()
+        h2.set_partition(side)
+        trs = h2.kl_run()
+    checks["kl_multi_equals_single"] = bool(tr["swaps"] == trs["swaps"] and np.array_equal(tr["node1"], trs["node1"])
+                                            and np.array_equal(tr["node2"], trs["node2"])
+                                            and np.array_equal(tr["cut"].view(np.uint32), trs["cut"].view(np.uint32))
+                                            and np.array_equal(tr["gain"].view(np.uint32), trs["gain"].view(np.uint32)))
+    ok = ok and checks["kl_multi_equals_single"]
+    print("MULTI", world, "lambda2", lam, "matvecs", st["matvecs"], "fiedler_ms %.2f" % st["ms_fiedler"], "kl_loop_ms %.2f" % st["ms_kl_loop"], checks, "OK" if ok else "FAIL", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 h.close()
