@@ -51,8 +51,10 @@ def full(rep, out, title):
                 if w in idx:
                     f.write(f"| {w} | {d[idx[w]]} | {units[idx[w]]} |\n")
             try:
-                rd = float(d[idx["dram__bytes_read.sum"]].replace(",", "")); wr = float(d[idx["dram__bytes_write.sum"]].replace(",", ""))
-                f.write(f"| traffic = dram read + write | {rd + wr:.3f} | {units[idx['dram__bytes_read.sum']]} |\n")
+                scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+                rd = float(d[idx["dram__bytes_read.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_read.sum"]]]
+                wr = float(d[idx["dram__bytes_write.sum"]].replace(",", "")) * scale[units[idx["dram__bytes_write.sum"]]]
+                f.write(f"| traffic = dram read + write | {(rd + wr) / 1e6:.3f} | Mbyte |\n")
             except Exception:
                 pass
             st = []
