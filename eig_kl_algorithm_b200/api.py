@@ -15,6 +15,7 @@ BIN_DIR = os.path.join(PKG, "bin")
 
 EIGKL_F_PROFILE = 0x1
 EIGKL_F_NO_GRAPH = 0x2
+EIGKL_F_PLAIN_LANCZOS = 0x4
 
 ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_FORMAT", -4: "E_CUDA", -5: "E_NCCL", -6: "E_NOCONV", -7: "E_NOMEM"}
 
@@ -49,6 +50,7 @@ class Stats(C.Structure):
                 ("nnz_laplacian", C.c_int64), ("nnz_kl", C.c_int64),
                 ("ncv", C.c_int32), ("matvecs", C.c_int32), ("restarts", C.c_int32), ("converged", C.c_int32),
                 ("resid_est", C.c_double * 2), ("lambda_", C.c_double * 2),
+                ("cheb_degree", C.c_int32), ("lanczos_steps", C.c_int32),
                 ("kl_swaps", C.c_int64), ("kl_cluster", C.c_int32), ("kl_threads", C.c_int32),
                 ("gpu_launches", C.c_int64),
                 ("ms_assemble_laplacian", C.c_double), ("ms_assemble_kl", C.c_double), ("ms_fiedler", C.c_double),

@@ -16,6 +16,7 @@
 #include "device_utils.cuh"
 #include "stl_order.h"
 #include <algorithm>
+#include <cstdlib>
 
 namespace eigkl {
 
@@ -252,17 +253,31 @@ __global__ void lap_fill_bwd_kernel(const int32_t *__restrict__ ua, const int32_
   val[pos] = -uwL[e];                                            // cEIG.cpp:115
 }
 // diagonal = -(sum of the row's off-diagonals, ascending column order)      cEIG.cpp:127-130
+// also reduces min / max of the diagonal (spectrum bounds for the Chebyshev filter of the Fiedler solve)
 __global__ void lap_diag_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ bstart, int32_t n,
-                                int32_t *__restrict__ col, double *__restrict__ val) {
+                                int32_t *__restrict__ col, double *__restrict__ val, unsigned long long *__restrict__ minmax) {
   int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= n) return;
-  const int32_t lo = rowptr[v], hi = rowptr[v + 1];
-  const int32_t dpos = lo + (bstart[v + 1] - bstart[v]);
-  double s = 0.0;
-  for (int32_t i = lo; i < hi; ++i)
-    if (i != dpos) s += val[i];
-  col[dpos] = v;
-  val[dpos] = -s;
+  unsigned long long kmin = 0ull, kmax = 0ull;      // max over ~orderable(d) == min over d
+  if (v < n) {
+    const int32_t lo = rowptr[v], hi = rowptr[v + 1];
+    const int32_t dpos = lo + (bstart[v + 1] - bstart[v]);
+    double s = 0.0;
+    for (int32_t i = lo; i < hi; ++i)
+      if (i != dpos) s += val[i];
+    col[dpos] = v;
+    val[dpos] = -s;
+    const unsigned long long k = double_orderable(-s);
+    kmin = ~k; kmax = k;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long a = __shfl_xor_sync(FULL_MASK, kmin, o), b = __shfl_xor_sync(FULL_MASK, kmax, o);
+    kmin = a > kmin ? a : kmin; kmax = b > kmax ? b : kmax;
+  }
+  if ((threadIdx.x & 31) == 0) { atomicMax(minmax, kmin); atomicMax(minmax + 1, kmax); }
+}
+__global__ void diag_decode_kernel(const unsigned long long *__restrict__ minmax, double *__restrict__ out) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = double_from_orderable(~minmax[0]); out[1] = double_from_orderable(minmax[1]); }
 }
 // blk_row[b] = first row r in [row_lo, row_hi] with rowptr[r] >= rowptr[row_lo] + b*chunk
 // (b in [0, n_blocks]; blk_row[n_blocks] = row_hi)
@@ -285,6 +300,7 @@ __global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t ro
 // over ~8 CTAs of 256 threads per SM in ONE wave, between 256 and 2048 non-zeros (the staging
 // capacities in spmv.cu / kl.cu are 4096).
 static int64_t pick_chunk(const eigkl_handle *h, int64_t nnz) {
+  if (const char *ev = getenv("EIGKL_CHUNK")) return std::max<int64_t>(64, atoll(ev));   // tuning aid
   const int64_t target_ctas = (int64_t)h->sm_count * 8;
   int64_t c = ceil_div(std::max<int64_t>(nnz, 1), target_ctas);
   c = ceil_div(c, 256) * 256;
@@ -312,7 +328,12 @@ void assemble_laplacian(eigkl_handle *h) {
     lap_fill_bwd_kernel<<<grid_for(U), TPB, 0, h->stream>>>(ue.a.p, ue.b.p, ue.wL.p, ue.perm_b.p, U, ue.bstart.p, L.rowptr.p, L.col.p, L.val.p);
     h->launches += 2;
   }
-  lap_diag_kernel<<<grid_for(n), TPB, 0, h->stream>>>(L.rowptr.p, ue.bstart.p, n, L.col.p, L.val.p);
+  L.diag_minmax.alloc(4);
+  EIGKL_CUDA(cudaMemsetAsync(L.diag_minmax.p, 0, 4 * sizeof(unsigned long long), h->stream));
+  lap_diag_kernel<<<grid_for(n), TPB, 0, h->stream>>>(L.rowptr.p, ue.bstart.p, n, L.col.p, L.val.p, L.diag_minmax.p);
+  diag_decode_kernel<<<1, 32, 0, h->stream>>>(L.diag_minmax.p, reinterpret_cast<double *>(L.diag_minmax.p + 2));
+  double dmm[2] = {0, 0};
+  EIGKL_CUDA(cudaMemcpyAsync(dmm, L.diag_minmax.p + 2, sizeof(dmm), cudaMemcpyDeviceToHost, h->stream));
   // this rank's row slice (the matrix itself is assembled in full on every rank: ~1 ms, and it keeps
   // the assembly free of collectives; SpMV and every vector are row-partitioned)
   int32_t n_pad = 0;
@@ -321,12 +342,13 @@ void assemble_laplacian(eigkl_handle *h) {
   EIGKL_CUDA(cudaMemcpyAsync(&rp[0], L.rowptr.p + L.row_lo, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaMemcpyAsync(&rp[1], L.rowptr.p + L.row_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  L.diag_min = dmm[0]; L.diag_max = dmm[1];
   const int64_t nnz_local = (int64_t)rp[1] - rp[0];
   const int64_t chunk = pick_chunk(h, nnz_local);
   L.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(nnz_local, chunk));
   L.blk_row.alloc((size_t)L.n_blocks + 1);
   row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, L.row_lo, L.row_hi, chunk, L.n_blocks, L.blk_row.p);
-  h->launches += 2;
+  h->launches += 3;
   EIGKL_CUDA(cudaGetLastError());
   L.valid = true;
   h->stats.nnz_laplacian = L.nnz;

@@ -150,6 +150,8 @@ struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, dia
   int32_t row_lo = 0, row_hi = 0;
   int32_t n_blocks = 0;
   DBuf<int32_t> blk_row;
+  DBuf<unsigned long long> diag_minmax;   // [0] = orderable(min L_ii) complemented, [1] = orderable(max L_ii)
+  double diag_min = 0, diag_max = 0;      // spectrum bounds: lambda_max <= 2 max L_ii, lambda_2 <= n/(n-1) min L_ii
   bool valid = false;
 };
 
@@ -187,7 +189,7 @@ struct EigState {
   size_t ld = 0;               // leading dimension of the basis (n rounded up)
   DBuf<double> V[2];           // two banks of ld*(ncv+1)
   int bank = 0;
-  DBuf<double> w[2];           // Lanczos work vector (double buffered)
+  DBuf<double> w[3];           // Lanczos / Chebyshev recurrence work vectors (rotating)
   DBuf<double> partial;        // multidot / norm partials
   DBuf<double> hcoef;          // 2*(ncv+1) : h of pass 1 and 2
   DBuf<double> alpha, beta;    // ncv each
@@ -258,9 +260,12 @@ void assemble_kl_graph(eigkl_handle *h);
 // ---- EIG (spmv.cu, lanczos.cu, eig_solver.cpp) ------------------------------------------------------
 void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scale_inv /*device or null*/,
                  double *store_scaled /*or null*/);
+void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const double *z, double *y, const double *scale_inv,
+                    double *store_scaled, double ca, double cb, double cg);
 void fiedler_solve(eigkl_handle *h);
 void partition_from_fiedler(eigkl_handle *h);
 void sym_eig(int n, double *a, double *evals);   // dense symmetric eigen-solver (host)
+void tridiag_top_eig(int n, const double *d, const double *e, int k, double *theta, double *Y);   // k largest pairs
 
 // ---- KL (kl.cu) ---------------------------------------------------------------------------------------
 void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *order0, int64_t n0,

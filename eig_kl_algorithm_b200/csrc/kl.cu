@@ -621,7 +621,10 @@ void kl_run(eigkl_handle *h) {
   p.mctrl = nullptr;
 
   int nc = h->opts.kl_cluster;
-  if (nc <= 0) nc = (n <= 4096) ? 1 : 8;
+  // measured (tools/kl_sweep.py): the swap loop is a chain of ~10 dependent L2 round trips, so up to
+  // ibm10's size one CTA (block barriers only) beats any cluster (11.6 vs 13.6 us/swap); the cluster only
+  // pays once the per-swap tile scan is large
+  if (nc <= 0) nc = (n <= 131072) ? 1 : 8;
   EIGKL_REQUIRE(nc == 1 || nc == 2 || nc == 4 || nc == 8 || nc == 16, EIGKL_E_ARG, "kl_cluster must be 1, 2, 4, 8 or 16");
   if (nc > 8) {
     EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_kernel<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));

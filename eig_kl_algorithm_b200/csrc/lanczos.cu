@@ -353,25 +353,37 @@ void launch_norm(LzCtx &c, const double *w) {
   }
 }
 
-// one Lanczos step j: x_local (this rank's slice of the un-normalised v_j, with *scale = 1/|v_j|) -> V[:, j];
-// leaves the un-normalised v_{j+1} slice in w_out and 1/beta_j in scal[1]
-void lanczos_step(LzCtx &c, double *V, int j, const double *x_local, const double *scale, bool store, double *w_out) {
+// full Gram-Schmidt (twice) of w against V[:, 0..j]; leaves alpha_j, beta_j, 1/beta_j on the device
+void orthogonalise(LzCtx &c, double *V, int j, double *w) {
   auto &e = c.h->eig;
-  const double *x = x_local;
-  if (c.R > 1) {                                                      // C1: SpMV halo exchange
-    comm_allgather_f64(c.h, x_local, e.xfull.p, c.ld);
-    x = e.xfull.p;
-  }
-  spmv_launch(c.h, x, w_out, scale, store ? V + (size_t)j * c.ld : nullptr);
   double *h1 = e.hcoef.p, *h2 = e.hcoef.p + (c.m + 1);
-  launch_multidot(c, V, j + 1, w_out, h1, 1);
-  launch_update(c, V, j + 1, w_out, h1, nullptr, j, 1);      // sets flag = 1 when the second pass can be skipped
-  launch_multidot(c, V, j + 1, w_out, h2, 2);
-  launch_update(c, V, j + 1, w_out, h2, h1, j, 2);
+  launch_multidot(c, V, j + 1, w, h1, 1);
+  launch_update(c, V, j + 1, w, h1, nullptr, j, 1);      // sets flag = 1 when the second pass can be skipped
+  launch_multidot(c, V, j + 1, w, h2, 2);
+  launch_update(c, V, j + 1, w, h2, h1, j, 2);
+}
+
+// gather source for an SpMV whose input is the rank-local slice xl
+const double *gathered(LzCtx &c, const double *xl) {
+  if (c.R == 1) return xl;
+  comm_allgather_f64(c.h, xl, c.h->eig.xfull.p, c.ld);                 // C1: SpMV halo exchange
+  return c.h->eig.xfull.p - 0;
 }
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------
+// The solve.  Lanczos runs on B = T_d((b + a - 2L)/(b - a)), the degree-d Chebyshev polynomial that maps
+// [a, b] onto [-1, 1]:  a = the Fiedler bound n/(n-1) * min_i L_ii >= lambda_2,  b = 2 max_i L_ii >=
+// lambda_max (Gershgorin).  B has the eigenvectors of L; the unwanted part of the spectrum is squeezed
+// into [-1, 1] while the wanted end (0, lambda_2) is amplified like cosh(d * acosh(.)), so the two
+// LARGEST pairs of B are the two smallest of L and Lanczos needs ~d times fewer steps.  The number of
+// SpMVs stays about the same, but the re-orthogonalisation traffic (4 * j * n * 8 bytes per step, 70% of
+// the unfiltered solve) shrinks by d.  d = 1 (EIGKL_F_PLAIN_LANCZOS) is plain Lanczos on (c - L)/e.
+// Each application of B is d SpMVs with the three-term recurrence fused into the SpMV epilogue.
+// lambda_2 and the Fiedler vector come from a Rayleigh-Ritz step on L itself over the two converged
+// Ritz vectors, and the true residual |L v - lambda v| is checked before returning.
+// ---------------------------------------------------------------------------------------------------
 void fiedler_solve(eigkl_handle *h) {
   auto &L = h->L;
   auto &e = h->eig;
@@ -379,10 +391,9 @@ void fiedler_solve(eigkl_handle *h) {
   const int32_t n = L.n;
   const int nev = 2;
   int m = h->opts.ncv > 0 ? h->opts.ncv : std::min(100, n / 2);        // cEIG.cpp:195
-  EIGKL_REQUIRE(m > nev && m <= n, EIGKL_E_ARG, "eigkl_fiedler: need nev < ncv <= n (graph too small)");
+  EIGKL_REQUIRE(m > nev + 1 && m <= n, EIGKL_E_ARG, "eigkl_fiedler: need nev + 1 < ncv <= n (graph too small)");
   const double tol = h->opts.tol > 0 ? h->opts.tol : 1e-10;
   const int maxit = h->opts.max_restarts > 0 ? h->opts.max_restarts : 1000;
-  const double eps23 = std::pow(DBL_EPSILON, 2.0 / 3.0);
   cudaStream_t st = h->stream;
 
   LzCtx c;
@@ -395,14 +406,26 @@ void fiedler_solve(eigkl_handle *h) {
   c.gx_md = (int)std::max<int64_t>(1, ceil_div(c.nl, MD_ROWS));
   c.gx_up = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(c.nl, UP_ROWS), 8 * h->sm_count));
   {
-    // second Gram-Schmidt pass only when |w_after| <= eta |w_before| (eta = 1/sqrt(2) is the classical
-    // "twice is enough" bound; EIGKL_DGKS_ETA overrides, 1.0 forces both passes every step)
+    // second Gram-Schmidt pass only when |w_after| <= eta |w_before| (eta = 1/sqrt(2): "twice is enough").
+    // Smaller eta was tried and is NOT safe here: with eta = 0.25 orthogonality degrades from 1e-11 to 1e-5
+    // within three restarts and the Ritz values turn negative.
     double eta = 0.70710678118654752;
     if (const char *ev = getenv("EIGKL_DGKS_ETA")) eta = atof(ev);
     c.eta2 = eta * eta;
   }
+  // ---- polynomial filter ----
+  int deg = (h->opts.flags & EIGKL_F_PLAIN_LANCZOS) ? 1 : 16;
+  if (const char *ev = getenv("EIGKL_CHEB_DEGREE")) deg = std::max(1, atoi(ev));
+  double fb = 2.0 * L.diag_max * (1.0 + 1e-9);
+  if (!(fb > 0.0)) fb = 1.0;                                           // graph without edges
+  double fa = std::max(L.diag_min * ((double)n / std::max(1, n - 1)) * 1.01, fb / 1024.0);
+  if (deg == 1) fa = 0.0;                                              // plain: B = (b/2 - L)/(b/2)
+  if (fa >= 0.5 * fb) fa = 0.5 * fb;
+  const double fc = 0.5 * (fb + fa), fe = 0.5 * (fb - fa);
+
   e.n = n; e.ncv = m; e.ld = c.ld;
-  for (int b = 0; b < 2; ++b) { e.V[b].ensure(c.ld * (size_t)(m + 1)); e.w[b].ensure(c.ld); }
+  for (int b = 0; b < 2; ++b) e.V[b].ensure(c.ld * (size_t)(m + 7));
+  for (int b = 0; b < 3; ++b) e.w[b].ensure(c.ld);
   e.partial.ensure((size_t)std::max<int64_t>((int64_t)c.gx_md * (m + 1), c.gx_up) + 8);
   e.hcoef.ensure(2 * (size_t)(m + 1));
   e.alpha.ensure((size_t)m); e.beta.ensure((size_t)m);
@@ -415,9 +438,10 @@ void fiedler_solve(eigkl_handle *h) {
   e.fiedler.ensure(c.ld * (size_t)c.R);
   if (c.R > 1) e.xfull.ensure(c.ld * (size_t)c.R);
   EIGKL_CUDA(cudaMemsetAsync(e.counters.p, 0, (size_t)n_counters * sizeof(unsigned int), st));
-  for (int b = 0; b < 2; ++b) EIGKL_CUDA(cudaMemsetAsync(e.w[b].p, 0, c.ld * sizeof(double), st));
+  for (int b = 0; b < 3; ++b) EIGKL_CUDA(cudaMemsetAsync(e.w[b].p, 0, c.ld * sizeof(double), st));
   const double one = 1.0;
   EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 2, &one, sizeof(double), cudaMemcpyHostToDevice, st));   // scal[2] = 1.0
+  const double *d_one = e.scal.p + 2;
 
   // start vector (Spectra: SimpleRandom residual, uniform in [-0.5, 0.5); ours is a seeded splitmix64 of the
   // GLOBAL row id, so the vector does not depend on the number of ranks)
@@ -427,102 +451,213 @@ void fiedler_solve(eigkl_handle *h) {
   }
   launch_norm(c, e.w[0].p);
 
-  std::vector<double> T((size_t)m * m, 0.0), Yh((size_t)m * m), theta(m), alpha(m), beta(m), Ycm;
+  // w = B x:  d SpMVs, recurrence fused.  x is either an un-normalised buffer (scale = 1/beta, v_j stored)
+  // or an already normalised basis column (after a restart).  Returns the index of the buffer holding w.
+  auto apply_filter = [&](const double *x_in, const double *scale, double *v_store, const double *v_norm, int avoid) -> int {
+    int o1 = (avoid + 1) % 3;
+    // y1 = s * (c x - L x) / e
+    spmv_launch_ex(h, gathered(c, x_in), x_in, nullptr, e.w[o1].p, scale, v_store, -1.0 / fe, fc / fe, 0.0);
+    const double *prev2 = v_norm;            // normalised v_j (= T_0 x)
+    int p1 = o1;
+    for (int kk = 2; kk <= deg; ++kk) {
+      int o = 0;
+      while (o == p1 || e.w[o].p == prev2) ++o;
+      // y_k = 2 (c y_{k-1} - L y_{k-1}) / e - y_{k-2}
+      spmv_launch_ex(h, gathered(c, e.w[p1].p), e.w[p1].p, prev2, e.w[o].p, d_one, nullptr, -2.0 / fe, 2.0 * fc / fe, -1.0);
+      prev2 = e.w[p1].p;
+      p1 = o;
+    }
+    return p1;
+  };
+
+  std::vector<double> T((size_t)m * m, 0.0), Yh((size_t)m * m), theta(m), alpha(m), beta(m), Ycm, off(m);
   int k = 0, cur = 0, bank = 0, it = 0, nmv = 0;
   double res[2] = {0, 0};
   bool converged = false;
-  double beta_m = 0.0;
-  for (it = 0; it < maxit; ++it) {
-    double *V = e.V[bank].p;
-    for (int j = k; j < m; ++j) {
-      if (j == k && it > 0) {
-        // right after a restart V[:, k] already holds the normalised v_m
-        lanczos_step(c, V, j, V + (size_t)k * c.ld, e.scal.p + 2, false, e.w[cur ^ 1].p);
-      } else {
-        lanczos_step(c, V, j, e.w[cur].p, e.scal.p + 1, true, e.w[cur ^ 1].p);
-      }
-      cur ^= 1;
-      ++nmv;
-    }
-    // v_m = w / beta_m into column m
-    if (c.nl > 0) {
-      scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[cur].p, e.scal.p + 1, V + (size_t)m * c.ld, c.nl);
-      h->launches++;
-    }
-    EIGKL_CUDA(cudaMemcpyAsync(alpha.data(), e.alpha.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EIGKL_CUDA(cudaMemcpyAsync(beta.data(), e.beta.p, (size_t)m * sizeof(double), cudaMemcpyDeviceToHost, st));
+  double beta_last = 0.0;
+  int jfin = m - 1;                          // last completed step of the final cycle
+  double tol_p = tol;                        // tolerance in the filtered space
+  const int check_every = 4;
+  std::vector<double> Ytop;                  // (jfin+1) x 2, column-major: the two wanted Ritz vectors in the basis
+  double th_top[2] = {0, 0};
+
+  // convergence test on the leading (jj x jj) block after step jj-1; fills Ytop / th_top
+  auto check = [&](int jj) -> bool {
+    EIGKL_CUDA(cudaMemcpyAsync(alpha.data(), e.alpha.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EIGKL_CUDA(cudaMemcpyAsync(beta.data(), e.beta.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
     EIGKL_CUDA(cudaStreamSynchronize(st));
-    for (int j = k; j < m; ++j) {
-      T[(size_t)j * m + j] = alpha[j];
-      if (j + 1 < m) { T[(size_t)j * m + j + 1] = beta[j]; T[(size_t)(j + 1) * m + j] = beta[j]; }
+    beta_last = beta[jj - 1];
+    EIGKL_REQUIRE(std::isfinite(beta_last), EIGKL_E_NOCONV, "eigkl_fiedler: Lanczos breakdown (non-finite beta)");
+    Ytop.assign((size_t)jj * 2, 0.0);
+    if (k == 0) {                            // still a plain tridiagonal: O(jj) per pair
+      tridiag_top_eig(jj, alpha.data(), beta.data(), 2, th_top, Ytop.data());
+    } else {
+      for (int j = k; j < jj; ++j) {
+        T[(size_t)j * m + j] = alpha[j];
+        if (j + 1 < m) { T[(size_t)j * m + j + 1] = beta[j]; T[(size_t)(j + 1) * m + j] = beta[j]; }
+      }
+      std::vector<double> A((size_t)jj * jj), ev(jj);
+      for (int r = 0; r < jj; ++r)
+        for (int q = 0; q < jj; ++q) A[(size_t)r * jj + q] = T[(size_t)r * m + q];
+      sym_eig(jj, A.data(), ev.data());
+      for (int t = 0; t < 2; ++t) {
+        th_top[t] = ev[jj - 1 - t];
+        for (int r = 0; r < jj; ++r) Ytop[(size_t)t * jj + r] = A[(size_t)r * jj + (jj - 1 - t)];
+      }
     }
-    beta_m = beta[m - 1];
-    EIGKL_REQUIRE(std::isfinite(beta_m), EIGKL_E_NOCONV, "eigkl_fiedler: Lanczos breakdown (non-finite beta)");
-    Yh = T;
-    sym_eig(m, Yh.data(), theta.data());
     int nconv = 0;
-    for (int i = 0; i < nev; ++i) {
-      res[i] = std::fabs(beta_m * Yh[(size_t)(m - 1) * m + i]);
-      if (res[i] < tol * std::max(eps23, std::fabs(theta[i]))) ++nconv;
+    for (int t = 0; t < nev; ++t) {
+      res[t] = std::fabs(beta_last * Ytop[(size_t)t * jj + (jj - 1)]);
+      if (res[t] < tol_p * std::max(std::fabs(th_top[t]), 1.0)) ++nconv;
     }
-    if (nconv == nev) { converged = true; ++it; break; }
-    if (it == maxit - 1) { ++it; break; }
-    int kk = h->opts.keep > 0 ? h->opts.keep : std::max(nev + nconv, m / 5);
-    kk = std::max(nev, std::min(kk, m - 2));
-    // V_new[:, 0:kk] = V[:, 0:m] Y[:, 0:kk];  V_new[:, kk] = v_m   (rank-local: no communication)
-    Ycm.assign((size_t)m * kk, 0.0);
-    for (int cc = 0; cc < kk; ++cc)
-      for (int j = 0; j < m; ++j) Ycm[(size_t)cc * m + j] = Yh[(size_t)j * m + cc];
+    return nconv == nev;
+  };
+
+  // Rayleigh-Ritz on L over the two Ritz vectors; returns the true residual of the Fiedler pair
+  double lam1 = 0, lam2 = 0;
+  auto extract = [&](int jj) -> double {
+    double *V = e.V[bank].p, *Vn = e.V[bank ^ 1].p;           // Vn columns 0,1 = X ; 2,3 = L X ; 4,5 = scratch
+    double *scratch = Vn + (size_t)4 * c.ld;
+    // the live Lanczos state (w buffers, 1/beta in scal[1]) must survive a rejected extraction
+    EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 4, e.scal.p + 1, sizeof(double), cudaMemcpyDeviceToDevice, st));
+    Ycm.assign((size_t)jj * 2, 0.0);
+    for (int t = 0; t < 2; ++t)
+      for (int r = 0; r < jj; ++r) Ycm[(size_t)t * jj + r] = Ytop[(size_t)t * jj + r];
     EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), Ycm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
-    double *Vn = e.V[bank ^ 1].p;
-    if (c.nl > 0) {
-      dim3 grid((unsigned)ceil_div(c.nl, LZ_THREADS), (unsigned)ceil_div(kk, RS_COLS));
-      h->prof.begin(KC_RESTART, st);
-      restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(V, c.ld, m, e.Y.p, kk, Vn, c.ld, c.nl);
-      h->prof.end(st);
-      h->launches++;
-    }
-    EIGKL_CUDA(cudaMemcpyAsync(Vn + (size_t)kk * c.ld, V + (size_t)m * c.ld, c.ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
-    EIGKL_CUDA(cudaStreamSynchronize(st));    // Ycm is reused next cycle
-    std::fill(T.begin(), T.end(), 0.0);
-    for (int cc = 0; cc < kk; ++cc) {
-      T[(size_t)cc * m + cc] = theta[cc];
-      const double s = beta_m * Yh[(size_t)(m - 1) * m + cc];
-      T[(size_t)kk * m + cc] = s;
-      T[(size_t)cc * m + kk] = s;
-    }
-    bank ^= 1;
-    k = kk;
-  }
-  // Ritz vector of the larger wanted value (index 1): cEIG.cpp:205-207 takes evalues(0)/evecs.col(0)
-  // of Spectra's descending result, i.e. lambda2
-  {
-    Ycm.assign((size_t)m, 0.0);
-    for (int j = 0; j < m; ++j) Ycm[j] = Yh[(size_t)j * m + 1];
-    EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), (size_t)m * sizeof(double), cudaMemcpyHostToDevice, st));
-    double *slice = (c.R > 1) ? e.w[1].p : e.fiedler.p;
     if (c.nl > 0) {
       dim3 grid((unsigned)ceil_div(c.nl, LZ_THREADS), 1);
-      restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(e.V[bank].p, c.ld, m, e.Y.p, 1, e.w[0].p, c.ld, c.nl);
+      restart_kernel<<<grid, LZ_THREADS, (size_t)jj * RS_COLS * sizeof(double), st>>>(V, c.ld, jj, e.Y.p, 2, Vn, c.ld, c.nl);
       h->launches++;
     }
-    launch_norm(c, e.w[0].p);
-    if (c.nl > 0) {
-      scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[0].p, e.scal.p + 1, slice, c.nl);
-      h->launches++;
+    double H[4] = {0, 0, 0, 0};
+    for (int t = 0; t < 2; ++t) {
+      const double *xt = Vn + (size_t)t * c.ld;
+      spmv_launch_ex(h, gathered(c, xt), xt, nullptr, Vn + (size_t)(2 + t) * c.ld, d_one, nullptr, 1.0, 0.0, 0.0);
+      launch_multidot(c, Vn, 2, Vn + (size_t)(2 + t) * c.ld, e.hcoef.p, 1);
+      EIGKL_CUDA(cudaMemcpyAsync(&H[2 * t], e.hcoef.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+      ++nmv;
+    }
+    EIGKL_CUDA(cudaStreamSynchronize(st));
+    // 2x2 symmetric eigenproblem  [[H0, H1], [H2, H3]]  (H1 ~ H2)
+    const double a11 = H[0], a22 = H[3], a12 = 0.5 * (H[1] + H[2]);
+    const double tr = 0.5 * (a11 + a22), df = 0.5 * (a11 - a22), rad = std::sqrt(df * df + a12 * a12);
+    lam1 = tr - rad; lam2 = tr + rad;
+    double z0, z1;                           // eigenvector of the LARGER value (lambda_2, cEIG.cpp:205-207)
+    if (std::fabs(a12) > 1e-300) { z0 = a12; z1 = lam2 - a11; }
+    else if (a11 >= a22) { z0 = 1.0; z1 = 0.0; }
+    else { z0 = 0.0; z1 = 1.0; }
+    const double zn = std::sqrt(z0 * z0 + z1 * z1);
+    z0 /= zn; z1 /= zn;
+    // v = X z  and  r = (L X) z - lambda_2 X z, both as 4-column combinations
+    const double cv[4] = {z0, z1, 0.0, 0.0}, cr[4] = {-lam2 * z0, -lam2 * z1, z0, z1};
+    double *slice = (c.R > 1) ? Vn + (size_t)5 * c.ld : e.fiedler.p;
+    double rnorm = 0.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, pass == 0 ? cr : cv, 4 * sizeof(double), cudaMemcpyHostToDevice, st));
+      if (c.nl > 0) {
+        dim3 grid((unsigned)ceil_div(c.nl, LZ_THREADS), 1);
+        restart_kernel<<<grid, LZ_THREADS, (size_t)4 * RS_COLS * sizeof(double), st>>>(Vn, c.ld, 4, e.Y.p, 1, scratch, c.ld, c.nl);
+        h->launches++;
+      }
+      launch_norm(c, scratch);
+      if (pass == 0) {
+        double s0 = 0.0;
+        EIGKL_CUDA(cudaMemcpyAsync(&s0, e.scal.p, sizeof(double), cudaMemcpyDeviceToHost, st));
+        EIGKL_CUDA(cudaStreamSynchronize(st));
+        rnorm = std::sqrt(s0);
+      } else if (c.nl > 0) {
+        scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(scratch, e.scal.p + 1, slice, c.nl);
+        h->launches++;
+      }
     }
     if (c.R > 1) comm_allgather_f64(h, slice, e.fiedler.p, c.ld);     // every rank ends with the full vector
+    EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 1, e.scal.p + 4, sizeof(double), cudaMemcpyDeviceToDevice, st));
     EIGKL_CUDA(cudaStreamSynchronize(st));
+    return rnorm;
+  };
+
+  double true_res = 0.0;
+  for (it = 0; it < maxit && !converged; ++it) {
+    double *V = e.V[bank].p;
+    bool cycle_done = false;
+    for (int j = k; j < m && !cycle_done; ++j) {
+      int wi;
+      if (j == k && it > 0) wi = apply_filter(V + (size_t)k * c.ld, d_one, nullptr, V + (size_t)k * c.ld, cur);   // normalised v_k
+      else wi = apply_filter(e.w[cur].p, e.scal.p + 1, V + (size_t)j * c.ld, V + (size_t)j * c.ld, cur);
+      nmv += deg;
+      cur = wi;
+      orthogonalise(c, V, j, e.w[cur].p);
+      const int jj = j + 1;
+      const bool at_end = (jj == m);
+      const bool do_check = at_end || (k == 0 && jj >= 8 && jj % check_every == 0);
+      if (do_check && check(jj)) {
+        jfin = j;
+        true_res = extract(jj);
+        // accept when the pair is a genuine eigenpair of L (the reference's criterion is the same
+        // relative 1e-10 on its own Ritz estimate); otherwise tighten the filtered tolerance and go on
+        const double accept = std::max(1e-9 * std::fabs(lam2), 1e-13 * fb);
+        if (true_res <= accept || tol_p < 1e-15) { converged = true; cycle_done = true; }
+        else tol_p *= 1e-2;
+      }
+      if (at_end) cycle_done = true;
+    }
+    if (converged) { ++it; break; }
+    if (it == maxit - 1) { ++it; break; }
+    // ---- thick restart: keep the `kk` LARGEST Ritz pairs of the filtered operator ----
+    {
+      for (int j = k; j < m; ++j) {
+        T[(size_t)j * m + j] = alpha[j];
+        if (j + 1 < m) { T[(size_t)j * m + j + 1] = beta[j]; T[(size_t)(j + 1) * m + j] = beta[j]; }
+      }
+      const double beta_m = beta[m - 1];
+      Yh = T;
+      sym_eig(m, Yh.data(), theta.data());
+      int kk = h->opts.keep > 0 ? h->opts.keep : std::max(nev + 1, m / 5);
+      kk = std::max(nev, std::min(kk, m - 2));
+      // v_m = w / beta_m into column m
+      if (c.nl > 0) {
+        scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[cur].p, e.scal.p + 1, V + (size_t)m * c.ld, c.nl);
+        h->launches++;
+      }
+      Ycm.assign((size_t)m * kk, 0.0);
+      for (int cc = 0; cc < kk; ++cc)
+        for (int j = 0; j < m; ++j) Ycm[(size_t)cc * m + j] = Yh[(size_t)j * m + (m - 1 - cc)];
+      EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), Ycm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+      double *Vn = e.V[bank ^ 1].p;
+      if (c.nl > 0) {
+        dim3 grid((unsigned)ceil_div(c.nl, LZ_THREADS), (unsigned)ceil_div(kk, RS_COLS));
+        h->prof.begin(KC_RESTART, st);
+        restart_kernel<<<grid, LZ_THREADS, (size_t)m * RS_COLS * sizeof(double), st>>>(V, c.ld, m, e.Y.p, kk, Vn, c.ld, c.nl);
+        h->prof.end(st);
+        h->launches++;
+      }
+      EIGKL_CUDA(cudaMemcpyAsync(Vn + (size_t)kk * c.ld, V + (size_t)m * c.ld, c.ld * sizeof(double), cudaMemcpyDeviceToDevice, st));
+      EIGKL_CUDA(cudaStreamSynchronize(st));    // Ycm is reused
+      std::fill(T.begin(), T.end(), 0.0);
+      for (int cc = 0; cc < kk; ++cc) {
+        T[(size_t)cc * m + cc] = theta[m - 1 - cc];
+        const double sv = beta_m * Yh[(size_t)(m - 1) * m + (m - 1 - cc)];
+        T[(size_t)kk * m + cc] = sv;
+        T[(size_t)cc * m + kk] = sv;
+      }
+      bank ^= 1;
+      k = kk;
+    }
+  }
+  if (!converged) {                          // hand back the best available pair anyway
+    check(jfin + 1);
+    true_res = extract(jfin + 1);
   }
   EIGKL_CUDA(cudaGetLastError());
-  e.lambda2 = theta[1];
+  e.lambda2 = lam2;
   e.have_vector = true;
   e.have_median = false;
   e.bank = bank;
-  auto &s = h->stats;
-  s.ncv = m; s.matvecs = nmv; s.restarts = it; s.converged = converged ? 1 : 0;
-  s.resid_est[0] = res[0]; s.resid_est[1] = res[1];
-  s.lambda[0] = theta[0]; s.lambda[1] = theta[1];
+  auto &sst = h->stats;
+  sst.ncv = m; sst.matvecs = nmv; sst.restarts = it; sst.converged = converged ? 1 : 0;
+  sst.resid_est[0] = res[1]; sst.resid_est[1] = true_res;
+  sst.lambda[0] = lam1; sst.lambda[1] = lam2;
+  sst.cheb_degree = deg; sst.lanczos_steps = (it > 0 ? (it - 1) * (m - k) : 0) + jfin + 1;
   if (!converged) throw Error(EIGKL_E_NOCONV, "eigkl_fiedler: not converged within max_restarts");
 }
 

@@ -12,8 +12,10 @@
 //     for high-degree rows (industry2's 100..900-entry rows) -- lanes stride the row, shuffle reduction.
 //     (ncu on ibm10: the staged variant stalls on mio_throttle/barrier and its 32 KB/CTA of shared memory
 //     leaves no L1 for the x gathers, which are 70% of the L2 sector traffic.)
-// Fused epilogue/prologue for Lanczos: y = (L x) * (*scale) and, optionally, v_store = x * (*scale)
-// for the block's own rows, so the basis vector v_j = w/beta is written by the SpMV that consumes it.
+// Fused epilogue for the (Chebyshev-filtered) Lanczos recurrence:
+//     y[r] = ca * s * (L x)[r] + cb * s * x[r] + cg * z[r],   s = *scale (1/beta of the previous step)
+// and, optionally, v_store[r] = s * x[r], so the three-term recurrence T_{k+1} = 2 t T_k - T_{k-1} and
+// the normalisation v_j = w/beta are applied by the SpMV itself (no separate axpy/scale kernels).
 // Bound: HBM (or L2 when the matrix fits the 126 MB L2): nnz*12 + n*20 bytes per launch.
 #include "internal.h"
 #include "device_utils.cuh"
@@ -23,31 +25,86 @@ namespace eigkl {
 constexpr int SPMV_THREADS = 256;
 constexpr int SPMV_STAGE = 4096;        // staging capacity in products (32 KB)
 
+struct SpmvEpilogue {
+  const double *xl;      // this rank's slice of x (row r at xl[r - off])
+  const double *z;       // slice of the vector two steps back in the recurrence (may be null)
+  double *y;             // output slice
+  double ca, cb, cg;     // already multiplied by *scale where the formula asks for it
+  int32_t off;
+  __device__ __forceinline__ void emit(int32_t r, double lx) const {
+    double out = ca * lx;
+    if (cb != 0.0) out += cb * xl[r - off];
+    if (z) out += cg * z[r - off];
+    y[r - off] = out;
+  }
+};
+
 // L lanes cooperate on one row: lanes stride the row (coalesced across the sub-warp and, because
 // consecutive sub-warps own consecutive rows, across the warp), then a shuffle reduction of width L.
+// Rows much longer than the block's mean (a 574-entry row among 20-entry rows in ibm10; the 900-entry rows
+// of industry2) would serialise dozens of dependent load rounds on a few lanes, so they are set aside in a
+// shared-memory list and handled afterwards by whole warps with 4 independent loads per lane in flight
+// (measured on industry2: 26.7 -> 14.4 us per SpMV; unrolling the sub-warp loop 4-fold in place instead
+// gave 28.7 us).
+constexpr int SPMV_MAX_LONG = 64;
 template <int L>
 __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                                              const double *__restrict__ val, const double *__restrict__ x,
-                                             double *__restrict__ y, int32_t r0, int32_t r1, double sc, int tid) {
+                                             const SpmvEpilogue &ep, int32_t r0, int32_t r1, int tid,
+                                             int32_t *long_rows, int *n_long) {
   constexpr int ROWS_PER_ITER = SPMV_THREADS / L;
+  constexpr int LONG_LEN = (L >= 32) ? 512 : 8 * L;
   const int sub = tid & (L - 1);
+  if (tid == 0) *n_long = 0;
+  __syncthreads();
   for (int32_t base = r0; base < r1; base += ROWS_PER_ITER) {      // block-uniform trip count
     const int32_t r = base + tid / L;
     double s = 0.0;
+    bool deferred = false;
     if (r < r1) {
       const int32_t lo = rowptr[r], hi = rowptr[r + 1];
-      int32_t i = lo + sub;
-      for (; i + L < hi; i += 2 * L) {                             // two independent gathers in flight
-        const double a0 = val[i], a1 = val[i + L];
-        const double x0 = __ldg(x + col[i]), x1 = __ldg(x + col[i + L]);
-        s += a0 * x0;
-        s += a1 * x1;
+      if (hi - lo > LONG_LEN) {
+        // only the lanes of this row's sub-warp are guaranteed to be here
+        const unsigned sub_mask = (L >= 32) ? FULL_MASK : (((1u << L) - 1u) << ((tid & 31) & ~(L - 1)));
+        int slot = SPMV_MAX_LONG;
+        if (sub == 0) slot = atomicAdd(n_long, 1);
+        slot = __shfl_sync(sub_mask, slot, (tid & 31) & ~(L - 1));
+        if (slot < SPMV_MAX_LONG) {
+          if (sub == 0) long_rows[slot] = r;
+          deferred = true;
+        }
       }
-      if (i < hi) s += val[i] * __ldg(x + col[i]);
+      if (!deferred) {
+        int32_t i = lo + sub;
+        for (; i + L < hi; i += 2 * L) {                           // two independent gathers in flight
+          const double a0 = val[i], a1 = val[i + L];
+          const double x0 = __ldg(x + col[i]), x1 = __ldg(x + col[i + L]);
+          s += a0 * x0;
+          s += a1 * x1;
+        }
+        if (i < hi) s += val[i] * __ldg(x + col[i]);
+      }
     }
 #pragma unroll
     for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
-    if (r < r1 && sub == 0) y[r] = s * sc;
+    if (r < r1 && sub == 0 && !deferred) ep.emit(r, s);
+  }
+  __syncthreads();
+  const int nl = min(*n_long, SPMV_MAX_LONG);
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int q = warp; q < nl; q += SPMV_THREADS / 32) {             // one warp per long row
+    const int32_t r = long_rows[q];
+    const int32_t lo = rowptr[r], hi = rowptr[r + 1];
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int32_t i = lo + lane;
+    for (; i + 96 < hi; i += 128) {
+      const double a0 = val[i], a1 = val[i + 32], a2 = val[i + 64], a3 = val[i + 96];
+      const int32_t c0 = col[i], c1 = col[i + 32], c2 = col[i + 64], c3 = col[i + 96];
+      s0 += a0 * __ldg(x + c0); s1 += a1 * __ldg(x + c1); s2 += a2 * __ldg(x + c2); s3 += a3 * __ldg(x + c3);
+    }
+    for (; i < hi; i += 32) s0 += val[i] * __ldg(x + col[i]);
+    const double s = warp_sum((s0 + s1) + (s2 + s3));
+    if (lane == 0) ep.emit(r, s);
   }
 }
 
@@ -55,23 +112,28 @@ __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr,
 // has row blocks short enough to want it, so that vector-only matrices keep their L1 for the x gathers).
 // mode: 0 = choose per row block, 1 = always stream (shared-memory staged), 2 = always sub-warp/warp per row
 template <bool WITH_STREAM>
-__global__ void __launch_bounds__(SPMV_THREADS)
+__global__ void __launch_bounds__(SPMV_THREADS, WITH_STREAM ? 4 : 8)    // 8 CTAs/SM: the row blocks are sized for ONE wave
 spmv_adaptive_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
-                     const double *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                     const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xl,
+                     const double *__restrict__ z, double *__restrict__ y,
                      const int32_t *__restrict__ blk_row, const double *__restrict__ scale,
-                     double *__restrict__ v_store, int32_t row_offset, int mode) {
+                     double *__restrict__ v_store, int32_t row_offset, int mode, double ca, double cb, double cg) {
   __shared__ double prod[WITH_STREAM ? SPMV_STAGE : 1];
+  __shared__ int32_t long_rows[SPMV_MAX_LONG];
+  __shared__ int n_long;
   const int tid = threadIdx.x;
   const int32_t r0 = blk_row[blockIdx.x], r1 = blk_row[blockIdx.x + 1];
   if (r0 >= r1) return;
   const double sc = scale ? __ldg(scale) : 1.0;
   const int32_t e0 = rowptr[r0], e1 = rowptr[r1];
   const int32_t span = e1 - e0, nrows = r1 - r0;
-  y -= row_offset;                       // rows are global ids; y and v_store are this rank's slices
+  // rows are global ids; xl, z, y and v_store are this rank's slices
+  const SpmvEpilogue ep{xl, z, y, ca * sc, cb * sc, cg, row_offset};
   if (v_store) {
-    for (int32_t r = r0 + tid; r < r1; r += SPMV_THREADS) v_store[r - row_offset] = __ldg(x + r) * sc;
+    for (int32_t r = r0 + tid; r < r1; r += SPMV_THREADS) v_store[r - row_offset] = xl[r - row_offset] * sc;
   }
-  const int mean = span / nrows;
+  int mean = span / nrows;
+  if (mode >= 100) mean = mode - 100;    // tuning aid: EIGKL_SPMV_MODE = 100 + forced mean row length
   const bool stream = WITH_STREAM && ((mode == 1) || (mode == 0 && mean < 4));
   if (stream && span <= SPMV_STAGE) {
 #pragma unroll 4
@@ -89,36 +151,44 @@ spmv_adaptive_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restri
         for (int32_t i = lo + sub; i < hi; i += tpr) s += prod[i];
       }
       for (int o = tpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
-      if (rr < nrows && sub == 0) y[r0 + rr] = s * sc;
+      if (rr < nrows && sub == 0) ep.emit(r0 + rr, s);
     }
   } else if (mean <= 4) {
-    rows_subwarp<2>(rowptr, col, val, x, y, r0, r1, sc, tid);
+    rows_subwarp<2>(rowptr, col, val, x, ep, r0, r1, tid, long_rows, &n_long);
   } else if (mean <= 8) {
-    rows_subwarp<4>(rowptr, col, val, x, y, r0, r1, sc, tid);
+    rows_subwarp<4>(rowptr, col, val, x, ep, r0, r1, tid, long_rows, &n_long);
   } else if (mean <= 16) {
-    rows_subwarp<8>(rowptr, col, val, x, y, r0, r1, sc, tid);
+    rows_subwarp<8>(rowptr, col, val, x, ep, r0, r1, tid, long_rows, &n_long);
   } else if (mean <= 48) {
-    rows_subwarp<16>(rowptr, col, val, x, y, r0, r1, sc, tid);
+    rows_subwarp<16>(rowptr, col, val, x, ep, r0, r1, tid, long_rows, &n_long);
   } else {
-    rows_subwarp<32>(rowptr, col, val, x, y, r0, r1, sc, tid);   // warp per row (industry2-class rows)
+    rows_subwarp<32>(rowptr, col, val, x, ep, r0, r1, tid, long_rows, &n_long);   // warp per row (industry2-class rows)
   }
 }
 
-// x: full-length vector (global column ids); y / store_scaled: this rank's row slice
-void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scale_inv, double *store_scaled) {
+// y = ca*s*(L x) + cb*s*x + cg*z for this rank's rows (s = *scale_inv or 1).
+//   xg: full-length x (global column ids, the gather source); xl: this rank's slice of the same vector;
+//   z, y, store_scaled: rank-local slices.
+void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const double *z, double *y, const double *scale_inv,
+                    double *store_scaled, double ca, double cb, double cg) {
   auto &L = h->L;
   EIGKL_REQUIRE(L.valid, EIGKL_E_ARG, "Laplacian not assembled");
   if (L.row_hi <= L.row_lo) return;
   h->prof.begin(KC_SPMV, h->stream);
   const bool with_stream = h->spmv_mode == 1 || (h->spmv_mode == 0 && L.nnz < 6 * (int64_t)L.n);
   if (with_stream)
-    spmv_adaptive_kernel<true><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, x, y, L.blk_row.p,
-                                                                                   scale_inv, store_scaled, L.row_lo, h->spmv_mode);
+    spmv_adaptive_kernel<true><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, xg, xl, z, y, L.blk_row.p,
+                                                                                   scale_inv, store_scaled, L.row_lo, h->spmv_mode, ca, cb, cg);
   else
-    spmv_adaptive_kernel<false><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, x, y, L.blk_row.p,
-                                                                                    scale_inv, store_scaled, L.row_lo, h->spmv_mode);
+    spmv_adaptive_kernel<false><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, xg, xl, z, y, L.blk_row.p,
+                                                                                    scale_inv, store_scaled, L.row_lo, h->spmv_mode, ca, cb, cg);
   h->prof.end(h->stream);
   h->launches++;
+}
+
+// plain product y = L x (x full-length, y the rank's slice)
+void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scale_inv, double *store_scaled) {
+  spmv_launch_ex(h, x, x + h->L.row_lo, nullptr, y, scale_inv, store_scaled, 1.0, 0.0, 0.0);
 }
 
 }  // namespace eigkl

@@ -56,7 +56,8 @@ typedef struct {
 } eigkl_opts;
 
 #define EIGKL_F_PROFILE   0x1u  /* bracket every kernel class with CUDA events (see eigkl_stats)  */
-#define EIGKL_F_NO_GRAPH  0x2u  /* launch Lanczos steps directly instead of replaying a CUDA graph */
+#define EIGKL_F_NO_GRAPH  0x2u  /* reserved                                                          */
+#define EIGKL_F_PLAIN_LANCZOS 0x4u /* no Chebyshev filter: Lanczos on L itself (degree-1 map), as Spectra does */
 
 /* per-call statistics.  Times are device times from CUDA events on the handle's stream, in ms.   */
 typedef struct {
@@ -67,8 +68,9 @@ typedef struct {
   int64_t  nnz_kl;                            /* symmetric off-diagonals of the KL graph           */
   /* Fiedler solve */
   int32_t  ncv, matvecs, restarts, converged;
-  double   resid_est[2];                      /* |beta_m * y_last| of the two wanted Ritz pairs    */
-  double   lambda[2];                         /* the two smallest Ritz values (ascending)          */
+  double   resid_est[2];                      /* [0] Ritz estimate |beta y_last| (filtered space), [1] TRUE |L v - lambda2 v| */
+  double   lambda[2];                         /* the two smallest eigenvalues found (ascending)    */
+  int32_t  cheb_degree, lanczos_steps;        /* filter degree (matvecs ~ steps * degree)          */
   /* KL */
   int64_t  kl_swaps;
   int32_t  kl_cluster, kl_threads;

@@ -37,6 +37,9 @@ int shim_read_eig(const char *path, int32_t n, uint8_t *side, char *err, int err
 int shim_sym_eig(int n, double *a, double *evals) {
   try { sym_eig(n, a, evals); return 0; } catch (const Error &e) { return e.code; }
 }
+int shim_tridiag_top(int n, const double *d, const double *e, int k, double *theta, double *Y) {
+  try { tridiag_top_eig(n, d, e, k, theta, Y); return 0; } catch (const Error &e2) { return e2.code; }
+}
 // product's order replay (stl_order.h), host instantiation
 void shim_stl_order(const uint32_t *keys, int32_t n, int32_t *order) {
   std::vector<int32_t> next((size_t)std::max(n, 1)), bkt(stl_final_buckets((uint32_t)n));

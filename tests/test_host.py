@@ -19,6 +19,7 @@ def shim():
     L.shim_write_eig.argtypes = [C.c_char_p, C.c_double, C.c_double, P(C.c_double), C.c_int32]
     L.shim_read_eig.argtypes = [C.c_char_p, C.c_int32, P(C.c_uint8), C.c_char_p, C.c_int]
     L.shim_sym_eig.argtypes = [C.c_int, P(C.c_double), P(C.c_double)]
+    L.shim_tridiag_top.argtypes = [C.c_int, P(C.c_double), P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
     return L
 
 
@@ -106,6 +107,26 @@ def test_dense_eig(shim, n):
     assert np.allclose(d, np.linalg.eigvalsh(a), atol=1e-12 * max(1.0, np.abs(a).max()) * n)
     assert np.abs(a @ z - z * d).max() < 1e-12 * n
     assert np.abs(z.T @ z - np.eye(n)).max() < 1e-12 * n
+
+
+@pytest.mark.parametrize("n", [2, 3, 10, 37, 100])
+def test_tridiag_top_eig(shim, n):
+    """Top-k pairs of a Lanczos-like tridiagonal (bisection + inverse iteration) vs numpy."""
+    rng = np.random.default_rng(100 + n)
+    d = rng.standard_normal(n) * 3 + np.linspace(5, -5, n)
+    e = np.abs(rng.standard_normal(max(n - 1, 1))) + 0.1
+    T = np.diag(d) + np.diag(e[: n - 1], 1) + np.diag(e[: n - 1], -1)
+    k = min(3, n)
+    th = np.zeros(k)
+    Y = np.zeros(n * k)
+    assert shim.shim_tridiag_top(n, _p(d, C.c_double), _p(e, C.c_double), k, _p(th, C.c_double), _p(Y, C.c_double)) == 0
+    w, V = np.linalg.eigh(T)
+    assert np.allclose(th, w[::-1][:k], atol=1e-12 * np.abs(w).max())
+    Y = Y.reshape(k, n).T
+    for t in range(k):
+        assert np.linalg.norm(T @ Y[:, t] - th[t] * Y[:, t]) < 1e-11 * np.abs(w).max()
+        assert abs(abs(Y[:, t] @ V[:, n - 1 - t]) - 1) < 1e-10
+    assert np.abs(Y.T @ Y - np.eye(k)).max() < 1e-10
 
 
 def test_trace_writer_format(eigkl_lib, tmp_path):

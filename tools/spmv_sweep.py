@@ -9,8 +9,14 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     h = api.Handle(); h.load_hgr(path); h.assemble_laplacian(); st = h.stats()
     warm = h.time_kernel("spmv", 50, False); cold = h.time_kernel("spmv", 20, True)
     b = st["bytes_spmv"]
-    print(f"{name:10s} mode={os.environ.get('EIGKL_SPMV_MODE','0')} n={st['n_nodes']} nnz={st['nnz_laplacian']} warm {warm*1e3:7.2f} us ({b/warm/1e6:7.0f} GB/s)  flushed {cold*1e3:7.2f} us ({b/cold/1e6:7.0f} GB/s)")
+    print(f"{name:10s} mode={os.environ.get('EIGKL_SPMV_MODE','0')} chunk={os.environ.get('EIGKL_CHUNK','auto')} n={st['n_nodes']} nnz={st['nnz_laplacian']} warm {warm*1e3:7.2f} us ({b/warm/1e6:7.0f} GB/s)  flushed {cold*1e3:7.2f} us ({b/cold/1e6:7.0f} GB/s)")
 else:
+    modes = os.environ.get("MODES", "0,1,2").split(",")
+    chunks = os.environ.get("CHUNKS", "").split(",")
     for name in sys.argv[1:]:
-        for mode in ("0", "1", "2"):
-            subprocess.run([sys.executable, __file__, "child", name], env=dict(os.environ, EIGKL_SPMV_MODE=mode))
+        for mode in modes:
+            for ch in chunks:
+                env = dict(os.environ, EIGKL_SPMV_MODE=mode)
+                if ch:
+                    env["EIGKL_CHUNK"] = ch
+                subprocess.run([sys.executable, __file__, "child", name], env=env)
