@@ -358,7 +358,7 @@ def main():
         kernels["spmv"] = cls("spmv", bytes_each=s1["bytes_spmv"])
         kernels["multidot"] = cls("multidot", bytes_total=s1["bytes_multidot_total"] - s0["bytes_multidot_total"])
         kernels["update"] = cls("update", bytes_total=s1["bytes_update_total"] - s0["bytes_update_total"])
-        kernels["restart"] = cls("restart", bytes_total=(s1["n_restart"] - s0["n_restart"]) * (s1["ncv"] + s1["ncv"] // 5) * n_nodes * 8.0)
+        kernels["restart"] = cls("restart", bytes_total=(s1["n_restart"] - s0["n_restart"]) * (s1["ncv"] + max(3, s1["ncv"] // 5)) * n_nodes * 8.0)
         kernels["dvalues"] = cls("dvalues", bytes_each=s1["bytes_dvalues"])
         kernels["kl_loop"] = {"launches": 1, "ms_total": s1["ms_kl_loop"], "swaps": s1["kl_swaps"],
                               "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]), "bound": "latency (cluster barriers), not bandwidth"}
@@ -380,8 +380,10 @@ def main():
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "us_avg": d["us_avg"], "launches_in_pass": d["launches"],
-                "note": "average over every launch of this kernel in one extra profiled pass (CUDA events on the library's stream); "
-                        "the working set of this circuit fits the 126 MB L2, so achieved can exceed the HBM copy peak"}
+                "note": "average over every launch of this kernel in one extra profiled pass (CUDA events around each launch on the "
+                        "library's stream; the events themselves add ~2 us per launch, see kernels.spmv_isolated for back-to-back timing). "
+                        "achieved = algorithmic bytes (nnz*12 + n*20 for SpMV) / time; the circuit is L2-resident and the SpMV is bound by the "
+                        "32-byte sectors of its 8-byte x gathers, not by HBM (DESIGN.md section 4)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -401,8 +403,9 @@ def main():
                 "config": {"workload": name, "nodes": n_nodes, "nets": n_nets, "pins": int(len(pins)),
                            "parallelism": ("Lanczos row-partitioned over %d ranks (NCCL halo all-gather + dot all-reduces); KL D-values/arg-max partitioned by node range with one NCCL max all-reduce per swap; O(1 ms) assembly replicated" % world) if world > 1 else "1 GPU",
                            "l2": "working set < L2: every step re-assembles and re-solves from the resident pins; inputs are not flushed between steps",
-                           "ncv": st["ncv"], "matvecs_per_pass": st["matvecs"], "restarts": st["restarts"], "kl_swaps": st["kl_swaps"],
-                           "kl_cluster": st["kl_cluster"]},
+                           "ncv": st["ncv"], "cheb_degree": st["cheb_degree"], "lanczos_steps": st["lanczos_steps"],
+                           "spmv_per_pass": st["matvecs"], "restarts": st["restarts"],
+                           "true_residual": st["resid_est"][1], "kl_swaps": st["kl_swaps"], "kl_cluster": st["kl_cluster"]},
                 "stage_ms": {"assemble_laplacian": st["ms_assemble_laplacian"], "fiedler_solve": st["ms_fiedler"],
                              "partition": st["ms_partition"], "assemble_kl": st["ms_assemble_kl"], "kl_setup": st["ms_kl_setup"],
                              "kl_loop": st["ms_kl_loop"]},

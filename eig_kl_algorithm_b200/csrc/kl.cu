@@ -348,22 +348,29 @@ float kl_cut0(eigkl_handle *h) {
 // ---------------------------------------------------------------------------------------------------
 // tile keys
 // ---------------------------------------------------------------------------------------------------
-// [lo, hi): the nodes this rank owns (everything on one GPU); other nodes of the tile are ignored
+// [lo, hi): the nodes this rank owns (everything on one GPU); other nodes of the tile are ignored.
+// All 24 loads of a lane are issued before the first use: one L2 round trip per rescan.
 __device__ __forceinline__ void tile_scan(const uint8_t *state, const float *val, const uint32_t *__restrict__ rank, int32_t lo,
                                           int32_t hi, int32_t tile, int lane, unsigned long long &k0, unsigned long long &k1) {
   k0 = 0ull; k1 = 0ull;
   const int32_t base = tile * KL_TILE;
+  unsigned st[KL_TILE / 32];
+  float vv[KL_TILE / 32];
+  uint32_t rk[KL_TILE / 32];
 #pragma unroll
   for (int r = 0; r < KL_TILE / 32; ++r) {
     const int32_t u = base + r * 32 + lane;
-    if (u >= lo && u < hi) {
-      const unsigned s = __ldcg(state + u);
-      if (!(s & ST_LOCK)) {
-        const float v = __ldcg(val + u);
-        const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - __ldg(rank + u));
-        if (s & ST_SIDE) { const unsigned long long key = ((unsigned long long)float_orderable(-v) << 32) | low; k1 = key > k1 ? key : k1; }
-        else             { const unsigned long long key = ((unsigned long long)float_orderable(v) << 32) | low;  k0 = key > k0 ? key : k0; }
-      }
+    const bool in = (u >= lo && u < hi);
+    st[r] = in ? (unsigned)__ldcg(state + u) : ST_LOCK;
+    vv[r] = in ? __ldcg(val + u) : 0.0f;
+    rk[r] = in ? __ldg(rank + u) : 0u;
+  }
+#pragma unroll
+  for (int r = 0; r < KL_TILE / 32; ++r) {
+    if (!(st[r] & ST_LOCK)) {
+      const unsigned long long low = (unsigned long long)(0xFFFFFFFFu - rk[r]);
+      if (st[r] & ST_SIDE) { const unsigned long long key = ((unsigned long long)float_orderable(-vv[r]) << 32) | low; k1 = key > k1 ? key : k1; }
+      else                 { const unsigned long long key = ((unsigned long long)float_orderable(vv[r]) << 32) | low;  k0 = key > k0 ? key : k0; }
     }
   }
   k0 = warp_max_u64(k0);
@@ -455,7 +462,6 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
 
   __shared__ unsigned long long red0[32], red1[32];
   __shared__ unsigned long long sh_best[2];
-  __shared__ float sh_w;
   __shared__ float sh_cut;
   __shared__ uint32_t sh_term, sh_iter;
   __shared__ int sh_done;
@@ -470,6 +476,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
     }
   }
   __syncthreads();
+  uint32_t it_local = sh_iter;
 
   while (!sh_done) {
     // ---- S1: best pair over the cached tile keys ------------------------------------------------
@@ -505,7 +512,6 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
       }
     }
     }   // !MULTI
-    if (tid == 0) sh_w = 0.0f;
     __syncthreads();
     const unsigned long long b0 = sh_best[0], b1 = sh_best[1];
     if (b0 == 0ull || b1 == 0ull) {                  // no selectable node on one side (cKL.cpp:387-389)
@@ -513,59 +519,85 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
       __syncthreads();
       break;
     }
+    ++it_local;                                      // swap number, kept in a register by every thread
     const int32_t a = __ldg(p.order0 + (0xFFFFFFFFu - (uint32_t)(b0 & 0xFFFFFFFFull)));
     const int32_t b = __ldg(p.order1 + (0xFFFFFFFFu - (uint32_t)(b1 & 0xFFFFFFFFull)));
     const int32_t alo = __ldg(p.rowptr + a), ahi = __ldg(p.rowptr + a + 1);
     const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
-    // ---- S2: gain, cut, trace, termination (every CTA computes the same values) --------------------
-    for (int32_t i = alo + tid; i < ahi; i += KL_LOOP_THREADS)
-      if (__ldg(p.col + i) == b) sh_w = __ldg(p.w + i);              // getEdgeWeight, cKL.cpp:75-82
-    __syncthreads();
-    if (tid == 0) {
-      const float maxGain = float_from_orderable((uint32_t)(b0 >> 32));
-      const float minGain = __fsub_rn(0.0f, float_from_orderable((uint32_t)(b1 >> 32)));
-      const float gain = __fsub_rn(__fsub_rn(maxGain, minGain), __fmul_rn(2.0f, sh_w));   // cKL.cpp:360
-      const float cut = __fsub_rn(sh_cut, gain);                                          // cKL.cpp:362
-      sh_cut = cut;
-      const uint32_t it = ++sh_iter;
-      if (cr == 0) {
-        p.t_cut[it] = cut; p.t_gain[it] = gain; p.t_n1[it] = a; p.t_n2[it] = b;
-        __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));          // swip, cKL.cpp:274-286
-        __stcg(p.state + b, (uint8_t)(ST_LOCK));
-      }
-      if (gain <= 0.0f) { if (++sh_term > p.term_limit) sh_done = 1; }   // cKL.cpp:382-386
-      else sh_term = 0;
-      if (--sh_rem0 == 0) sh_done = 1;
-      if (--sh_rem1 == 0) sh_done = 1;
-    }
-    // ---- S3: recompute D of every neighbour of a or b from scratch (cKL.cpp:253-272) -----------------
     const int32_t da = ahi - alo, items = da + (bhi - blo);
-    for (int32_t it = gwarp; it < items; it += total_warps) {
-      const int32_t v = __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
-      if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;       // another rank owns this D-value
-      const float nv = warp_row_value(p.col, p.w, p.state, __ldg(p.rowptr + v), __ldg(p.rowptr + v + 1), a, b, lane);
-      if (lane == 0) __stcg(p.val + v, nv);
-    }
-    cluster.sync();
-    // ---- S4: rescan the tiles that contain a touched node -----------------------------------------
-    const uint32_t stamp = sh_iter;
-    for (int32_t it = gwarp; it < items + 2; it += total_warps) {
-      int32_t v;
-      if (it < da) v = __ldg(p.col + alo + it);
-      else if (it < items) v = __ldg(p.col + blo + (it - da));
-      else v = (it == items) ? a : b;
-      if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;
-      const int32_t tile = v / KL_TILE;
-      unsigned claimed = 0;
-      if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
-      claimed = __shfl_sync(FULL_MASK, claimed, 0);
-      if (claimed) {
-        unsigned long long t0, t1;
-        tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, tile, lane, t0, t1);
-        if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
+    constexpr int WORKERS = KL_LOOP_THREADS / 32 - 1;    // warp 31 of every CTA is the bookkeeper
+    const unsigned gworker = cr * WORKERS + warp, total_workers = nc * WORKERS;
+    int32_t vkeep[4];
+    if (warp == WORKERS) {
+      // ---- S2 (off the critical path): gain, cut, trace, termination.  Every CTA's bookkeeper computes
+      //      the same values; CTA 0's also publishes them.
+      float wab = 0.0f;
+      for (int32_t i = alo + lane; i < ahi; i += 32)
+        if (__ldg(p.col + i) == b) wab = __ldg(p.w + i);             // getEdgeWeight, cKL.cpp:75-82
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wab = fmaxf(wab, __shfl_xor_sync(FULL_MASK, wab, o));   // weights are > 0
+      if (lane == 0) {
+        const float maxGain = float_from_orderable((uint32_t)(b0 >> 32));
+        const float minGain = __fsub_rn(0.0f, float_from_orderable((uint32_t)(b1 >> 32)));
+        const float gain = __fsub_rn(__fsub_rn(maxGain, minGain), __fmul_rn(2.0f, wab));    // cKL.cpp:360
+        const float cut = __fsub_rn(sh_cut, gain);                                          // cKL.cpp:362
+        sh_cut = cut;
+        sh_iter = it_local;
+        if (cr == 0) {
+          p.t_cut[it_local] = cut; p.t_gain[it_local] = gain; p.t_n1[it_local] = a; p.t_n2[it_local] = b;
+          __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));        // swip, cKL.cpp:274-286
+          __stcg(p.state + b, (uint8_t)(ST_LOCK));
+        }
+        if (gain <= 0.0f) { if (++sh_term > p.term_limit) sh_done = 1; }   // cKL.cpp:382-386
+        else sh_term = 0;
+        if (--sh_rem0 == 0) sh_done = 1;
+        if (--sh_rem1 == 0) sh_done = 1;
+      }
+    } else {
+      // ---- S3: recompute D of every neighbour of a or b from scratch (cKL.cpp:253-272) ---------------
+      int kept = 0;
+      for (int32_t it = gworker; it < items; it += total_workers, ++kept) {
+        const int32_t v = __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
+        if (kept < 4) vkeep[kept] = v;
+        if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;     // another rank owns this D-value
+        const float nv = warp_row_value(p.col, p.w, p.state, __ldg(p.rowptr + v), __ldg(p.rowptr + v + 1), a, b, lane);
+        if (lane == 0) __stcg(p.val + v, nv);
       }
     }
-    cluster.sync();
+    if (nc == 1) __syncthreads(); else cluster.sync();   // one CTA: a block barrier orders the .cg accesses
+    // ---- S4: rescan the tiles that contain a touched node (the bookkeeper takes the tiles of a and b) ----
+    const uint32_t stamp = it_local;
+    if (warp == WORKERS) {
+      for (int q = 0; q < 2; ++q) {
+        const int32_t v = q ? b : a;
+        if (cr != 0 || (MULTI && (v < p.own_lo || v >= p.own_hi))) continue;
+        const int32_t tile = v / KL_TILE;
+        unsigned claimed = 0;
+        if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
+        claimed = __shfl_sync(FULL_MASK, claimed, 0);
+        if (claimed) {
+          unsigned long long t0, t1;
+          tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, tile, lane, t0, t1);
+          if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
+        }
+      }
+    } else {
+      int kept = 0;
+      for (int32_t it = gworker; it < items; it += total_workers, ++kept) {
+        const int32_t v = (kept < 4) ? vkeep[kept] : __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
+        if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;
+        const int32_t tile = v / KL_TILE;
+        unsigned claimed = 0;
+        if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
+        claimed = __shfl_sync(FULL_MASK, claimed, 0);
+        if (claimed) {
+          unsigned long long t0, t1;
+          tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, tile, lane, t0, t1);
+          if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
+        }
+      }
+    }
+    if (nc == 1) __syncthreads(); else cluster.sync();
     if (MULTI) break;                                  // one swap per launch
   }
   if (cr == 0 && tid == 0) {

@@ -77,12 +77,12 @@ __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr,
       if (!deferred) {
         int32_t i = lo + sub;
         for (; i + L < hi; i += 2 * L) {                           // two independent gathers in flight
-          const double a0 = val[i], a1 = val[i + L];
-          const double x0 = __ldg(x + col[i]), x1 = __ldg(x + col[i + L]);
+          const double a0 = __ldcs(val + i), a1 = __ldcs(val + i + L);          // matrix: streamed (evict-first),
+          const double x0 = __ldg(x + __ldcs(col + i)), x1 = __ldg(x + __ldcs(col + i + L));   // x: kept in L1
           s += a0 * x0;
           s += a1 * x1;
         }
-        if (i < hi) s += val[i] * __ldg(x + col[i]);
+        if (i < hi) s += __ldcs(val + i) * __ldg(x + __ldcs(col + i));
       }
     }
 #pragma unroll
@@ -98,11 +98,11 @@ __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr,
     double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     int32_t i = lo + lane;
     for (; i + 96 < hi; i += 128) {
-      const double a0 = val[i], a1 = val[i + 32], a2 = val[i + 64], a3 = val[i + 96];
-      const int32_t c0 = col[i], c1 = col[i + 32], c2 = col[i + 64], c3 = col[i + 96];
+      const double a0 = __ldcs(val + i), a1 = __ldcs(val + i + 32), a2 = __ldcs(val + i + 64), a3 = __ldcs(val + i + 96);
+      const int32_t c0 = __ldcs(col + i), c1 = __ldcs(col + i + 32), c2 = __ldcs(col + i + 64), c3 = __ldcs(col + i + 96);
       s0 += a0 * __ldg(x + c0); s1 += a1 * __ldg(x + c1); s2 += a2 * __ldg(x + c2); s3 += a3 * __ldg(x + c3);
     }
-    for (; i < hi; i += 32) s0 += val[i] * __ldg(x + col[i]);
+    for (; i < hi; i += 32) s0 += __ldcs(val + i) * __ldg(x + __ldcs(col + i));
     const double s = warp_sum((s0 + s1) + (s2 + s3));
     if (lane == 0) ep.emit(r, s);
   }
