@@ -380,8 +380,8 @@ def main():
         roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
                 "frac": d["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
                 "us_avg": d["us_avg"], "launches_in_pass": d["launches"],
-                "note": "average over every launch of this kernel in one extra profiled pass (CUDA events around each launch on the "
-                        "library's stream; the events themselves add ~2 us per launch, see kernels.spmv_isolated for back-to-back timing). "
+                "note": "average over every launch of this kernel in one extra profiled pass on the same resident data (CUDA events on the "
+                        "library's stream; the SpMVs of one Chebyshev filter application, 16 back-to-back launches, share one event pair). "
                         "achieved = algorithmic bytes (nnz*12 + n*20 for SpMV) / time; the circuit is L2-resident and the SpMV is bound by the "
                         "32-byte sectors of its 8-byte x gathers, not by HBM (DESIGN.md section 4)"}
 

@@ -8,18 +8,19 @@ using namespace eigkl;
 
 namespace eigkl {
 
-void KernelProfiler::begin(int c, cudaStream_t s) {
-  if (!on) return;
+void KernelProfiler::begin(int c, cudaStream_t s, int w) {
+  if (!on || suppress) return;
   if (used + 2 > ev.size()) {
     const size_t old = ev.size();
     ev.resize(old + 4096);
     for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]);
   }
   cls.push_back(c);
+  weight.push_back(w);
   cudaEventRecord(ev[used], s);
 }
 void KernelProfiler::end(cudaStream_t s) {
-  if (!on) return;
+  if (!on || suppress) return;
   cudaEventRecord(ev[used + 1], s);
   used += 2;
 }
@@ -28,10 +29,11 @@ void KernelProfiler::resolve() {
   cudaEventSynchronize(ev[used - 1]);
   for (size_t i = 0; i < used; i += 2) {
     float t = 0.f;
-    if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) { ms[cls[i / 2]] += t; cnt[cls[i / 2]] += 1; }
+    if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) { ms[cls[i / 2]] += t; cnt[cls[i / 2]] += weight[i / 2]; }
   }
   used = 0;
   cls.clear();
+  weight.clear();
 }
 void KernelProfiler::reset() {
   resolve();

@@ -105,10 +105,12 @@ struct KernelProfiler {
   bool on = false;
   std::vector<cudaEvent_t> ev;   // pairs
   std::vector<int> cls;
+  std::vector<int> weight;       // launches covered by the pair (a group of back-to-back launches of one class)
+  int suppress = 0;              // >0: inner begin/end calls are ignored (the caller brackets a group)
   size_t used = 0;
   double ms[8] = {0};
   int64_t cnt[8] = {0};
-  void begin(int c, cudaStream_t s);
+  void begin(int c, cudaStream_t s, int w = 1);
   void end(cudaStream_t s);
   void resolve();
   void reset();

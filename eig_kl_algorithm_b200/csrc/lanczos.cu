@@ -454,6 +454,10 @@ void fiedler_solve(eigkl_handle *h) {
   // w = B x:  d SpMVs, recurrence fused.  x is either an un-normalised buffer (scale = 1/beta, v_j stored)
   // or an already normalised basis column (after a restart).  Returns the index of the buffer holding w.
   auto apply_filter = [&](const double *x_in, const double *scale, double *v_store, const double *v_norm, int avoid) -> int {
+    // profiling brackets the whole chain of `deg` back-to-back SpMVs with ONE event pair (single rank), so the
+    // ~2 us an event pair costs is not charged to every 15 us launch
+    const bool group = h->prof.on && c.R == 1;
+    if (group) { h->prof.begin(KC_SPMV, st, deg); h->prof.suppress++; }
     int o1 = (avoid + 1) % 3;
     // y1 = s * (c x - L x) / e
     spmv_launch_ex(h, gathered(c, x_in), x_in, nullptr, e.w[o1].p, scale, v_store, -1.0 / fe, fc / fe, 0.0);
@@ -467,6 +471,7 @@ void fiedler_solve(eigkl_handle *h) {
       prev2 = e.w[p1].p;
       p1 = o;
     }
+    if (group) { h->prof.suppress--; h->prof.end(st); }
     return p1;
   };
 
