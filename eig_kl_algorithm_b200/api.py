@@ -27,6 +27,7 @@ SYMBOLS = [
     "eigkl_assemble_laplacian", "eigkl_fiedler", "eigkl_partition_from_fiedler", "eigkl_write_eig",
     "eigkl_assemble_kl_graph", "eigkl_set_partition", "eigkl_set_partition_ordered", "eigkl_load_eig",
     "eigkl_kl_run", "eigkl_write_trace", "eigkl_get_partition", "eigkl_spmv", "eigkl_dvalues", "eigkl_cut",
+    "eigkl_get_kl_values",
     "eigkl_get_laplacian", "eigkl_get_kl_graph", "eigkl_time_kernel",
 ]
 
@@ -118,6 +119,7 @@ def load_library(path=LIB_PATH):
     L.eigkl_spmv.argtypes = [H, P(C.c_double), P(C.c_double)]
     L.eigkl_dvalues.argtypes = [H, P(C.c_float)]
     L.eigkl_cut.argtypes = [H, P(C.c_float)]
+    L.eigkl_get_kl_values.argtypes = [H, P(C.c_float)]
     L.eigkl_get_laplacian.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_double)]
     L.eigkl_get_kl_graph.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_float)]
     L.eigkl_time_kernel.argtypes = [H, C.c_int, C.c_int, C.c_int, P(C.c_double)]
@@ -286,6 +288,11 @@ class Handle:
     def dvalues(self):
         v = np.empty(self.n_nodes, np.float32)
         self._check(self.lib.eigkl_dvalues(self._h, _ptr(v, C.c_float)))
+        return v
+
+    def kl_values(self):
+        v = np.empty(self.n_nodes, np.float32)
+        self._check(self.lib.eigkl_get_kl_values(self._h, _ptr(v, C.c_float)))
         return v
 
     def cut(self):

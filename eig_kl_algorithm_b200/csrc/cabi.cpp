@@ -400,6 +400,15 @@ int eigkl_dvalues(eigkl_handle *h, float *val) {
   });
 }
 
+int eigkl_get_kl_values(eigkl_handle *h, float *val) {
+  return guarded(h, [&] {
+    EIGKL_REQUIRE(val && h->A.valid && h->kl.have_partition, EIGKL_E_ARG, "eigkl_get_kl_values: no KL state");
+    EIGKL_CUDA(cudaSetDevice(h->device));
+    EIGKL_CUDA(cudaMemcpyAsync(val, h->kl.val.p, (size_t)h->A.n * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
 int eigkl_cut(eigkl_handle *h, float *cut) {
   return guarded(h, [&] {
     EIGKL_REQUIRE(cut, EIGKL_E_ARG, "cut is NULL");

@@ -173,6 +173,8 @@ int  eigkl_get_partition(eigkl_handle *h, uint8_t *side);
 int  eigkl_spmv(eigkl_handle *h, const double *x, double *y);                 /* y = L x (host buffers) */
 int  eigkl_dvalues(eigkl_handle *h, float *val);       /* connections() for every node, cKL.cpp:225-251 */
 int  eigkl_cut(eigkl_handle *h, float *cut);           /* calCutSize() on one thread, cKL.cpp:199-223   */
+/* the D-values as the swap loop left them (nodeGains[] after KL(), cKL.cpp:40,270) -- no recomputation  */
+int  eigkl_get_kl_values(eigkl_handle *h, float *val);
 /* device copies of the assembled matrices (any pointer may be NULL); sizes from eigkl_get_stats   */
 int  eigkl_get_laplacian(eigkl_handle *h, int32_t *rowptr, int32_t *col, double *val);
 int  eigkl_get_kl_graph(eigkl_handle *h, int32_t *rowptr, int32_t *fwd_end, int32_t *col, float *w);

@@ -262,3 +262,59 @@ def test_fused_pipeline_equals_file_handoff(handles, oracle, circuits, tmp_path)
     h.load_eig(out)
     tr2 = h.kl_run()
     assert np.array_equal(tr2["node1"], tr["node1"]) and np.array_equal(tr2["cut"], tr["cut"])
+
+
+def test_plain_lanczos_flag_matches_filtered(handles, oracle, workdir):
+    """EIGKL_F_PLAIN_LANCZOS (Lanczos on L itself, the Spectra-style iteration) and the default Chebyshev-filtered
+    solver must agree with each other and with the golden file."""
+    c = "ibm01"
+    g = oracle.read_eig(datasets.golden_eig_path(workdir, c), handles[c].n_nodes)
+    out = {}
+    for name, flags in (("filtered", 0), ("plain", api.EIGKL_F_PLAIN_LANCZOS)):
+        with api.Handle(flags=flags) as h:
+            h.load_hgr(os.path.join(workdir, "circuit", c + ".hgr"))
+            h.assemble_laplacian()
+            lam, v = h.fiedler()
+            st = h.stats()
+            out[name] = (lam, v, st)
+            assert st["converged"] == 1 and st["cheb_degree"] == (1 if flags else 16)
+            assert abs(lam - g["lambda2"]) / g["lambda2"] <= 1e-8
+            cs = abs(v @ g["vec"]) / np.linalg.norm(g["vec"])
+            assert np.sqrt(max(0.0, 1.0 - cs * cs)) <= 1e-6
+    assert abs(out["plain"][0] - out["filtered"][0]) <= 1e-10 * out["plain"][0]
+    assert abs(abs(out["plain"][1] @ out["filtered"][1]) - 1.0) < 1e-12
+    assert out["filtered"][2]["lanczos_steps"] * 4 < out["plain"][2]["lanczos_steps"]     # the point of the filter
+
+
+@pytest.mark.parametrize("n", [8, 12, 31])
+def test_tiny_graphs(n, oracle, tmp_path):
+    """Smallest sizes the reference's ncv = min(100, n/2) rule allows: a ring of 2-pin nets plus one chord net."""
+    nets = [[i, (i + 1) % n] for i in range(n)] + [[0, n // 2, n // 3]]
+    path = str(tmp_path / "ring.hgr")
+    with open(path, "w") as f:
+        f.write(f"{len(nets)} {n}\n")
+        for e in nets:
+            f.write(" ".join(str(p + 1) for p in e) + "\n")
+    o = oracle.OracleEIG(oracle.OracleHgr(path))
+    L = np.zeros((n, n))
+    for r in range(n):
+        for e in range(o.rowptr[r], o.rowptr[r + 1]):
+            L[r, o.col[e]] = o.val[e]
+    w, V = np.linalg.eigh(L)
+    with api.Handle() as h:
+        h.load_hgr(path)
+        h.assemble_laplacian()
+        lam, v = h.fiedler()
+        assert abs(lam - w[1]) <= 1e-9 * w[1]
+        assert np.linalg.norm(L @ v - lam * v) < 1e-9
+        med, side = h.partition_from_fiedler()
+        h.assemble_kl_graph()
+        tr = h.kl_run()
+        ro = oracle.OracleKL(oracle.OracleHgr(path)).run(side)
+        assert np.array_equal(tr["node1"], ro["node1"]) and np.array_equal(tr["cut"].view(np.uint32), ro["cut"].view(np.uint32))
+    with api.Handle() as h:                           # below the reference's minimum: refused, not mis-solved
+        h.set_pins(4, np.array([0, 2, 4], np.int64), np.array([0, 1, 2, 3], np.int32))
+        h.assemble_laplacian()
+        with pytest.raises(api.EigklError) as e:
+            h.fiedler()
+        assert e.value.code == -1
