@@ -16,6 +16,7 @@ BIN_DIR = os.path.join(PKG, "bin")
 EIGKL_F_PROFILE = 0x1
 EIGKL_F_NO_GRAPH = 0x2
 EIGKL_F_PLAIN_LANCZOS = 0x4
+EIGKL_F_NATURAL_ORDER = 0x8
 
 ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_FORMAT", -4: "E_CUDA", -5: "E_NCCL", -6: "E_NOCONV", -7: "E_NOMEM"}
 
@@ -27,7 +28,7 @@ SYMBOLS = [
     "eigkl_assemble_laplacian", "eigkl_fiedler", "eigkl_partition_from_fiedler", "eigkl_write_eig",
     "eigkl_assemble_kl_graph", "eigkl_set_partition", "eigkl_set_partition_ordered", "eigkl_load_eig",
     "eigkl_kl_run", "eigkl_write_trace", "eigkl_get_partition", "eigkl_spmv", "eigkl_dvalues", "eigkl_cut",
-    "eigkl_get_kl_values",
+    "eigkl_get_kl_values", "eigkl_get_node_order",
     "eigkl_get_laplacian", "eigkl_get_kl_graph", "eigkl_time_kernel",
 ]
 
@@ -121,6 +122,7 @@ def load_library(path=LIB_PATH):
     L.eigkl_cut.argtypes = [H, P(C.c_float)]
     L.eigkl_get_kl_values.argtypes = [H, P(C.c_float)]
     L.eigkl_get_laplacian.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_double)]
+    L.eigkl_get_node_order.argtypes = [H, P(C.c_int32)]
     L.eigkl_get_kl_graph.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_int32), P(C.c_float)]
     L.eigkl_time_kernel.argtypes = [H, C.c_int, C.c_int, C.c_int, P(C.c_double)]
     for s in SYMBOLS:
@@ -314,6 +316,11 @@ class Handle:
         val = np.empty(nnz, np.float64)
         self._check(self.lib.eigkl_get_laplacian(self._h, _ptr(rp, C.c_int32), _ptr(col, C.c_int32), _ptr(val, C.c_double)))
         return rp, col, val
+
+    def node_order(self):
+        perm = np.empty(self.n_nodes, np.int32)
+        self._check(self.lib.eigkl_get_node_order(self._h, _ptr(perm, C.c_int32)))
+        return perm
 
     def get_kl_graph(self):
         st = self.stats()

@@ -140,6 +140,8 @@ void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t
   auto &g = h->hg;
   g.loaded = false;
   h->ue.valid = false;
+  h->ueL.valid = false;
+  h->order.valid = false;
   h->L.valid = false;
   h->A.valid = false;
   h->kl.have_partition = false;
@@ -167,9 +169,8 @@ void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t
   h->stats.n_nodes = n_nodes; h->stats.n_nets = n_nets; h->stats.n_pins = n_pins; h->stats.n_pairs = P;
 }
 
-void build_unique_edges(eigkl_handle *h) {
+void build_unique_edges(eigkl_handle *h, UniqueEdges &ue, const int32_t *pins) {
   auto &g = h->hg;
-  auto &ue = h->ue;
   EIGKL_REQUIRE(g.loaded, EIGKL_E_ARG, "no hypergraph loaded");
   if (ue.valid) return;
   const int64_t P = g.n_pairs;
@@ -183,7 +184,7 @@ void build_unique_edges(eigkl_handle *h) {
   EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
   int64_t U = 0;
   if (P > 0) {
-    expand_pairs_kernel<<<grid_for(P), TPB, 0, h->stream>>>(g.net_off.p, g.pins.p, g.pair_off.p, g.n_nets, P, nb, keys[0], vals[0], err.p);
+    expand_pairs_kernel<<<grid_for(P), TPB, 0, h->stream>>>(g.net_off.p, pins, g.pair_off.p, g.n_nets, P, nb, keys[0], vals[0], err.p);
     h->launches++;
     const int cur = radix_sort_kv(h, keys, vals, P, 2 * nb);
     auto &flag = h->scr.i32a; flag.alloc((size_t)P + 1);
@@ -297,19 +298,83 @@ __global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t ro
 
 // Row-block size in non-zeros.  The circuits here are small next to a B200 (ibm01: 0.23 M non-zeros vs
 // 0.3 M resident threads), so the kernels are latency bound: the chunk is sized to spread the matrix
-// over ~8 CTAs of 256 threads per SM in ONE wave, between 256 and 2048 non-zeros (the staging
-// capacities in spmv.cu / kl.cu are 4096).
-static int64_t pick_chunk(const eigkl_handle *h, int64_t nnz) {
+// over the CTAs resident at once (6 per SM for the SpMV kernel, 8 for the D-value kernel) in ONE wave,
+// between 256 and 2048 non-zeros (the staging capacities in spmv.cu / kl.cu are 4096).
+static int64_t pick_chunk(const eigkl_handle *h, int64_t nnz, int ctas_per_sm) {
   if (const char *ev = getenv("EIGKL_CHUNK")) return std::max<int64_t>(64, atoll(ev));   // tuning aid
-  const int64_t target_ctas = (int64_t)h->sm_count * 8;
+  const int64_t target_ctas = (int64_t)h->sm_count * ctas_per_sm;
   int64_t c = ceil_div(std::max<int64_t>(nnz, 1), target_ctas);
   c = ceil_div(c, 256) * 256;
   return std::min<int64_t>(2048, std::max<int64_t>(256, c));
 }
 
+// ---- node order of the EIG stage ---------------------------------------------------------------------
+// The x gathers of the SpMV are its traffic: in the file's numbering nearly every gather of ibm10 is a new
+// 32-byte sector (0.88 distinct sectors per non-zero within 128 consecutive rows).  Numbering the nodes by
+// the first net that mentions them puts net-mates next to each other: 0.17 distinct sectors per non-zero
+// (reverse Cuthill-McKee gives 0.18 and costs a BFS), i.e. the gathers hit L1 instead of L2.
+__global__ void first_net_kernel(const int64_t *__restrict__ net_off, const int32_t *__restrict__ pins, int32_t n_nets,
+                                 int64_t n_pins, uint32_t *__restrict__ first) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= n_pins) return;
+  int32_t lo = 0, hi = n_nets;            // last e with net_off[e] <= p
+  while (hi - lo > 1) {
+    int32_t mid = (lo + hi) >> 1;
+    if (net_off[mid] <= p) lo = mid; else hi = mid;
+  }
+  atomicMin(&first[pins[p]], (uint32_t)lo);
+}
+__global__ void order_keys_kernel(const uint32_t *__restrict__ first, int32_t n, uint32_t n_nets, unsigned long long *__restrict__ keys,
+                                  uint32_t *__restrict__ vals) {
+  int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) { keys[v] = (unsigned long long)min(first[v], n_nets); vals[v] = (uint32_t)v; }   // isolated nodes last
+}
+__global__ void order_finish_kernel(const uint32_t *__restrict__ sorted, int32_t n, int32_t *__restrict__ perm, int32_t *__restrict__ inv) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const int32_t v = (int32_t)sorted[i]; perm[i] = v; inv[v] = i; }
+}
+__global__ void identity_order_kernel(int32_t n, int32_t *__restrict__ perm, int32_t *__restrict__ inv) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { perm[i] = i; inv[i] = i; }
+}
+__global__ void relabel_pins_kernel(const int32_t *__restrict__ pins, const int32_t *__restrict__ inv, int64_t n_pins, int32_t *__restrict__ out) {
+  int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < n_pins) out[p] = inv[pins[p]];
+}
+
+static void build_node_order(eigkl_handle *h) {
+  auto &g = h->hg;
+  auto &o = h->order;
+  if (o.valid) return;
+  const int32_t n = g.n_nodes;
+  o.active = !(h->opts.flags & EIGKL_F_NATURAL_ORDER) && g.n_pins > 0;
+  o.perm.alloc((size_t)n); o.inv.alloc((size_t)n);
+  if (!o.active) {
+    identity_order_kernel<<<grid_for(n), TPB, 0, h->stream>>>(n, o.perm.p, o.inv.p);
+    h->launches++;
+    o.valid = true;
+    return;
+  }
+  o.first.alloc((size_t)n); o.pins.alloc((size_t)g.n_pins);
+  auto &e = h->eig;
+  for (int i = 0; i < 2; ++i) { e.sortkey[i].ensure((size_t)std::max<int64_t>(g.n_pairs, n) + 1); e.sortval[i].ensure((size_t)std::max<int64_t>(g.n_pairs, n) + 1); }
+  unsigned long long *keys[2] = {e.sortkey[0].p, e.sortkey[1].p};
+  uint32_t *vals[2] = {e.sortval[0].p, e.sortval[1].p};
+  EIGKL_CUDA(cudaMemsetAsync(o.first.p, 0xFF, (size_t)n * sizeof(uint32_t), h->stream));
+  first_net_kernel<<<grid_for(g.n_pins), TPB, 0, h->stream>>>(g.net_off.p, g.pins.p, g.n_nets, g.n_pins, o.first.p);
+  order_keys_kernel<<<grid_for(n), TPB, 0, h->stream>>>(o.first.p, n, (uint32_t)g.n_nets, keys[0], vals[0]);
+  const int cur = radix_sort_kv(h, keys, vals, n, bits_for((uint64_t)std::max(g.n_nets, 1)));
+  order_finish_kernel<<<grid_for(n), TPB, 0, h->stream>>>(vals[cur], n, o.perm.p, o.inv.p);
+  relabel_pins_kernel<<<grid_for(g.n_pins), TPB, 0, h->stream>>>(g.pins.p, o.inv.p, g.n_pins, o.pins.p);
+  h->launches += 4;
+  EIGKL_CUDA(cudaGetLastError());
+  o.valid = true;
+}
+
 void assemble_laplacian(eigkl_handle *h) {
-  build_unique_edges(h);
-  auto &ue = h->ue;
+  build_node_order(h);
+  auto &ue = h->order.active ? h->ueL : h->ue;
+  build_unique_edges(h, ue, h->order.active ? h->order.pins.p : h->hg.pins.p);
   auto &L = h->L;
   const int32_t n = h->hg.n_nodes;
   const int64_t U = ue.U;
@@ -344,7 +409,7 @@ void assemble_laplacian(eigkl_handle *h) {
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   L.diag_min = dmm[0]; L.diag_max = dmm[1];
   const int64_t nnz_local = (int64_t)rp[1] - rp[0];
-  const int64_t chunk = pick_chunk(h, nnz_local);
+  const int64_t chunk = pick_chunk(h, nnz_local, 6);
   L.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(nnz_local, chunk));
   L.blk_row.alloc((size_t)L.n_blocks + 1);
   row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, L.row_lo, L.row_hi, chunk, L.n_blocks, L.blk_row.p);
@@ -418,7 +483,7 @@ __global__ void kl_fill_bwd_kernel(const int32_t *__restrict__ ua, const int32_t
 }
 
 void assemble_kl_graph(eigkl_handle *h) {
-  build_unique_edges(h);
+  build_unique_edges(h, h->ue, h->hg.pins.p);
   auto &ue = h->ue;
   auto &A = h->A;
   const int32_t n = h->hg.n_nodes;
@@ -456,7 +521,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   } else {
     EIGKL_CUDA(cudaMemsetAsync(A.fwd_end.p, 0, (size_t)n * sizeof(int32_t), h->stream));
   }
-  const int64_t chunk = pick_chunk(h, A.nnz);
+  const int64_t chunk = pick_chunk(h, A.nnz, 8);
   A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz, chunk));
   A.blk_row.alloc((size_t)A.n_blocks + 1);
   row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, 0, n, chunk, A.n_blocks, A.blk_row.p);

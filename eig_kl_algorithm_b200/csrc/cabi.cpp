@@ -208,6 +208,8 @@ int eigkl_invalidate(eigkl_handle *h) {
     EIGKL_CUDA(cudaSetDevice(h->device));
     EIGKL_CUDA(cudaStreamSynchronize(h->stream));
     h->ue.valid = false;
+    h->ueL.valid = false;
+    h->order.valid = false;
     h->L.valid = false;
     h->A.valid = false;
     h->kl.have_partition = false;
@@ -379,13 +381,19 @@ int eigkl_spmv(eigkl_handle *h, const double *x, double *y) {
     row_partition(h->L.n, h->opts.nranks, h->opts.rank, &lo, &hi, &n_pad);
     const size_t full = (size_t)n_pad * (size_t)h->opts.nranks;
     DBuf<double> dx, dy, dg; dx.alloc(n); dy.alloc((size_t)n_pad); dg.alloc(full);
-    EIGKL_CUDA(cudaMemcpyAsync(dx.p, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    std::vector<int32_t> perm(n);
+    EIGKL_CUDA(cudaMemcpyAsync(perm.data(), h->order.perm.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+    std::vector<double> xp(n), yp(n);
+    for (size_t i = 0; i < n; ++i) xp[i] = x[perm[i]];                // file ids -> the matrix's node order
+    EIGKL_CUDA(cudaMemcpyAsync(dx.p, xp.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     EIGKL_CUDA(cudaMemsetAsync(dy.p, 0, (size_t)n_pad * sizeof(double), h->stream));
     spmv_launch(h, dx.p, dy.p, nullptr, nullptr);             // this rank's rows
     const double *src = dy.p;
     if (h->opts.nranks > 1) { comm_allgather_f64(h, dy.p, dg.p, (size_t)n_pad); src = dg.p; }
-    EIGKL_CUDA(cudaMemcpyAsync(y, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EIGKL_CUDA(cudaMemcpyAsync(yp.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+    for (size_t i = 0; i < n; ++i) y[perm[i]] = yp[i];
     EIGKL_CUDA(cudaGetLastError());
   });
 }
@@ -425,6 +433,15 @@ int eigkl_get_laplacian(eigkl_handle *h, int32_t *rowptr, int32_t *col, double *
     if (rowptr) EIGKL_CUDA(cudaMemcpyAsync(rowptr, L.rowptr.p, ((size_t)L.n + 1) * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (col) EIGKL_CUDA(cudaMemcpyAsync(col, L.col.p, (size_t)L.nnz * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     if (val) EIGKL_CUDA(cudaMemcpyAsync(val, L.val.p, (size_t)L.nnz * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  });
+}
+
+int eigkl_get_node_order(eigkl_handle *h, int32_t *perm) {
+  return guarded(h, [&] {
+    EIGKL_REQUIRE(perm && h->order.valid, EIGKL_E_ARG, "eigkl_get_node_order: assemble the Laplacian first");
+    EIGKL_CUDA(cudaSetDevice(h->device));
+    EIGKL_CUDA(cudaMemcpyAsync(perm, h->order.perm.p, (size_t)h->hg.n_nodes * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   });
 }

@@ -142,6 +142,17 @@ struct UniqueEdges {           // result of sort + segmented reduce: unique pair
   bool valid = false;
 };
 
+// node relabelling used by the EIG stage only (the KL stage keeps the file's ids: its fp32 summation order
+// and tie-breaks are defined by them): nodes sorted by the first net that mentions them
+struct NodeOrder {
+  DBuf<int32_t> perm;          // new id -> file id
+  DBuf<int32_t> inv;           // file id -> new id
+  DBuf<int32_t> pins;          // the pins relabelled
+  DBuf<uint32_t> first;        // scratch: first net of every node
+  bool active = false;         // false: identity (EIGKL_F_NATURAL_ORDER)
+  bool valid = false;
+};
+
 struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, diagonal included
   int32_t n = 0;
   int64_t nnz = 0;
@@ -200,7 +211,8 @@ struct EigState {
   DBuf<int> flag;              // [0] = 1: second Gram-Schmidt pass of the current step is skipped
   DBuf<double> Y;              // ncv*ncv restart coefficients (column major, ld = ncv)
   DBuf<double> xfull;          // nranks * n_pad : all-gathered SpMV input (multi-rank only)
-  DBuf<double> fiedler;        // n (nranks * n_pad when multi-rank) : result vector
+  DBuf<double> fiedler;        // n : result vector, file node ids
+  DBuf<double> fiedler_perm;   // n (nranks * n_pad when multi-rank) : result vector in the solver's node order
   DBuf<uint8_t> side;          // n : partition from the Fiedler vector
   DBuf<unsigned long long> sortkey[2];
   DBuf<uint32_t> sortval[2];
@@ -221,7 +233,9 @@ struct eigkl_handle {
   eigkl::StageTimer timer;
   eigkl::KernelProfiler prof;
   eigkl::Hypergraph hg;
-  eigkl::UniqueEdges ue;
+  eigkl::UniqueEdges ue;       // edges in the file's node ids (KL graph; Laplacian when the order is natural)
+  eigkl::UniqueEdges ueL;      // edges in the relabelled ids (Laplacian)
+  eigkl::NodeOrder order;
   eigkl::LaplacianCsr L;
   eigkl::KlCsr A;
   eigkl::KlState kl;
@@ -255,7 +269,7 @@ int bits_for(uint64_t max_value);
 
 // ---- assembly (assemble.cu) ------------------------------------------------------------------------
 void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t *net_off, const int32_t *pins);
-void build_unique_edges(eigkl_handle *h);       // sort + segmented reduce over net pins (shared by L and A)
+void build_unique_edges(eigkl_handle *h, UniqueEdges &ue, const int32_t *pins);   // sort + segmented reduce over net pins
 void assemble_laplacian(eigkl_handle *h);
 void assemble_kl_graph(eigkl_handle *h);
 

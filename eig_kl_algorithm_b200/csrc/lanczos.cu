@@ -252,6 +252,11 @@ norm_kernel(const double *__restrict__ w, int32_t n, double *__restrict__ partia
   if (threadIdx.x == 0) { scal[0] = s; scal[1] = s > 0.0 ? 1.0 / sqrt(s) : 0.0; }
 }
 
+// out[perm[i]] = in[i] : the solver's node order -> the file's node ids
+__global__ void unpermute_kernel(const double *__restrict__ in, const int32_t *__restrict__ perm, double *__restrict__ out, int32_t n) {
+  int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[perm[i]] = in[i];
+}
 __global__ void scale_store_kernel(const double *__restrict__ w, const double *__restrict__ scale, double *__restrict__ out, int32_t n) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = w[i] * __ldg(scale);
@@ -435,7 +440,9 @@ void fiedler_solve(eigkl_handle *h) {
   const int n_counters = 8 + (m + 1 + MD_COLS - 1) / MD_COLS + 1;
   e.counters.ensure((size_t)n_counters);
   e.Y.ensure((size_t)m * m);
-  e.fiedler.ensure(c.ld * (size_t)c.R);
+  e.fiedler.ensure((size_t)n);
+  e.fiedler_perm.ensure(c.ld * (size_t)c.R);
+  EIGKL_REQUIRE(h->order.valid, EIGKL_E_ARG, "node order missing");
   if (c.R > 1) e.xfull.ensure(c.ld * (size_t)c.R);
   EIGKL_CUDA(cudaMemsetAsync(e.counters.p, 0, (size_t)n_counters * sizeof(unsigned int), st));
   for (int b = 0; b < 3; ++b) EIGKL_CUDA(cudaMemsetAsync(e.w[b].p, 0, c.ld * sizeof(double), st));
@@ -555,7 +562,7 @@ void fiedler_solve(eigkl_handle *h) {
     z0 /= zn; z1 /= zn;
     // v = X z  and  r = (L X) z - lambda_2 X z, both as 4-column combinations
     const double cv[4] = {z0, z1, 0.0, 0.0}, cr[4] = {-lam2 * z0, -lam2 * z1, z0, z1};
-    double *slice = (c.R > 1) ? Vn + (size_t)5 * c.ld : e.fiedler.p;
+    double *slice = (c.R > 1) ? Vn + (size_t)5 * c.ld : e.fiedler_perm.p;
     double rnorm = 0.0;
     for (int pass = 0; pass < 2; ++pass) {
       EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, pass == 0 ? cr : cv, 4 * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -575,7 +582,9 @@ void fiedler_solve(eigkl_handle *h) {
         h->launches++;
       }
     }
-    if (c.R > 1) comm_allgather_f64(h, slice, e.fiedler.p, c.ld);     // every rank ends with the full vector
+    if (c.R > 1) comm_allgather_f64(h, slice, e.fiedler_perm.p, c.ld);     // every rank ends with the full vector
+    unpermute_kernel<<<(unsigned)ceil_div(n, LZ_THREADS), LZ_THREADS, 0, st>>>(e.fiedler_perm.p, h->order.perm.p, e.fiedler.p, n);
+    h->launches++;
     EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 1, e.scal.p + 4, sizeof(double), cudaMemcpyDeviceToDevice, st));
     EIGKL_CUDA(cudaStreamSynchronize(st));
     return rnorm;

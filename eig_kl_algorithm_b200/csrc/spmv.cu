@@ -31,12 +31,16 @@ struct SpmvEpilogue {
   double *y;             // output slice
   double ca, cb, cg;     // already multiplied by *scale where the formula asks for it
   int32_t off;
-  __device__ __forceinline__ void emit(int32_t r, double lx) const {
-    double out = ca * lx;
-    if (cb != 0.0) out += cb * xl[r - off];
-    if (z) out += cg * z[r - off];
-    y[r - off] = out;
+  // the row's own x and z values: loaded when the row starts, so that they are not one more dependent
+  // round trip after the reduction
+  __device__ __forceinline__ double prefetch(int32_t r) const {
+    double t = 0.0;
+    if (cb != 0.0) t = cb * xl[r - off];
+    if (z) t += cg * z[r - off];
+    return t;
   }
+  __device__ __forceinline__ void emit(int32_t r, double lx, double pre) const { y[r - off] = ca * lx + pre; }
+  __device__ __forceinline__ void emit(int32_t r, double lx) const { emit(r, lx, prefetch(r)); }
 };
 
 // L lanes cooperate on one row: lanes stride the row (coalesced across the sub-warp and, because
@@ -59,10 +63,11 @@ __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr,
   __syncthreads();
   for (int32_t base = r0; base < r1; base += ROWS_PER_ITER) {      // block-uniform trip count
     const int32_t r = base + tid / L;
-    double s = 0.0;
+    double s = 0.0, pre = 0.0;
     bool deferred = false;
     if (r < r1) {
       const int32_t lo = rowptr[r], hi = rowptr[r + 1];
+      if (sub == 0) pre = ep.prefetch(r);
       if (hi - lo > LONG_LEN) {
         // only the lanes of this row's sub-warp are guaranteed to be here
         const unsigned sub_mask = (L >= 32) ? FULL_MASK : (((1u << L) - 1u) << ((tid & 31) & ~(L - 1)));
@@ -87,7 +92,7 @@ __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr,
     }
 #pragma unroll
     for (int o = L >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(FULL_MASK, s, o);
-    if (r < r1 && sub == 0 && !deferred) ep.emit(r, s);
+    if (r < r1 && sub == 0 && !deferred) ep.emit(r, s, pre);
   }
   __syncthreads();
   const int nl = min(*n_long, SPMV_MAX_LONG);
@@ -112,7 +117,7 @@ __device__ __forceinline__ void rows_subwarp(const int32_t *__restrict__ rowptr,
 // has row blocks short enough to want it, so that vector-only matrices keep their L1 for the x gathers).
 // mode: 0 = choose per row block, 1 = always stream (shared-memory staged), 2 = always sub-warp/warp per row
 template <bool WITH_STREAM>
-__global__ void __launch_bounds__(SPMV_THREADS, WITH_STREAM ? 4 : 8)    // 8 CTAs/SM: the row blocks are sized for ONE wave
+__global__ void __launch_bounds__(SPMV_THREADS, WITH_STREAM ? 4 : 6)    // 6 CTAs/SM (<= 42 registers): the row blocks are sized for ONE wave
 spmv_adaptive_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
                      const double *__restrict__ val, const double *__restrict__ x, const double *__restrict__ xl,
                      const double *__restrict__ z, double *__restrict__ y,

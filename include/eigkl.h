@@ -57,6 +57,7 @@ typedef struct {
 
 #define EIGKL_F_PROFILE   0x1u  /* bracket every kernel class with CUDA events (see eigkl_stats)  */
 #define EIGKL_F_NO_GRAPH  0x2u  /* reserved                                                          */
+#define EIGKL_F_NATURAL_ORDER 0x8u /* EIG stage keeps the file's node numbering (default: nodes renumbered by first net, for gather locality) */
 #define EIGKL_F_PLAIN_LANCZOS 0x4u /* no Chebyshev filter: Lanczos on L itself (degree-1 map), as Spectra does */
 
 /* per-call statistics.  Times are device times from CUDA events on the handle's stream, in ms.   */
@@ -177,6 +178,9 @@ int  eigkl_cut(eigkl_handle *h, float *cut);           /* calCutSize() on one th
 int  eigkl_get_kl_values(eigkl_handle *h, float *val);
 /* device copies of the assembled matrices (any pointer may be NULL); sizes from eigkl_get_stats   */
 int  eigkl_get_laplacian(eigkl_handle *h, int32_t *rowptr, int32_t *col, double *val);
+/* the matrix above is stored in the EIG stage's node order: perm[new id] = file id (identity with
+ * EIGKL_F_NATURAL_ORDER).  Every other entry point takes and returns vectors in the file's ids.          */
+int  eigkl_get_node_order(eigkl_handle *h, int32_t *perm);
 int  eigkl_get_kl_graph(eigkl_handle *h, int32_t *rowptr, int32_t *fwd_end, int32_t *col, float *w);
 /* runs `iters` back-to-back launches of one kernel class on resident data and returns the average
  * device time per launch in ms (CUDA events on the handle's stream).  what: 0 = SpMV, 1 = D-values.

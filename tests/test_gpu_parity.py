@@ -45,20 +45,42 @@ def test_kl_graph_layout_bit_exact(c, handles, oracle, circuits):
     assert np.array_equal(w.view(np.uint32), o.w.view(np.uint32))   # fp32 sums in file order, bit for bit
 
 
-@pytest.mark.parametrize("c", CIRCUITS)
-def test_laplacian_matches_oracle(c, handles, oracle, circuits):
-    h = handles[c]
-    h.assemble_laplacian()
+def _laplacian_in_file_ids(h):
+    """The assembled matrix is stored in the EIG stage's node order; bring it back to the file's ids."""
+    import scipy.sparse as sp
     rp, col, val = h.get_laplacian()
+    perm = h.node_order()
+    n = h.n_nodes
+    rows = np.repeat(np.arange(n), np.diff(rp))
+    a = sp.coo_matrix((val, (perm[rows], perm[col])), shape=(n, n)).tocsr()
+    a.sort_indices()
+    return a, perm
+
+
+@pytest.mark.parametrize("c", CIRCUITS)
+@pytest.mark.parametrize("natural", [False, True])
+def test_laplacian_matches_oracle(c, natural, oracle, circuits):
     o = oracle.OracleEIG(oracle.OracleHgr(circuits[c]))
-    assert np.array_equal(rp, o.rowptr.astype(np.int32))
-    assert np.array_equal(col, o.col)
-    assert np.array_equal(val, o.val)                       # same fp64 sums in the same (file) order
-    x = np.random.default_rng(0).standard_normal(h.n_nodes)
-    y = h.spmv(x)
-    yo = o.spmv(x)
-    assert np.abs(y - yo).max() <= 1e-12 * np.abs(yo).max()
-    assert np.abs(h.spmv(np.ones(h.n_nodes))).max() < 1e-13 * np.abs(val).max() * 64   # L 1 = 0 up to row round-off
+    with api.Handle(flags=api.EIGKL_F_NATURAL_ORDER if natural else 0) as h:
+        h.load_hgr(circuits[c])
+        h.assemble_laplacian()
+        a, perm = _laplacian_in_file_ids(h)
+        assert sorted(perm.tolist()) == list(range(h.n_nodes))
+        assert natural == bool(np.array_equal(perm, np.arange(h.n_nodes)))
+        assert np.array_equal(a.indptr, o.rowptr.astype(a.indptr.dtype))
+        assert np.array_equal(a.indices, o.col)
+        rows = np.repeat(np.arange(h.n_nodes), np.diff(a.indptr))
+        offd = rows != a.indices
+        assert np.array_equal(a.data[offd], o.val[offd])        # same fp64 sums in the same (file) order
+        # the diagonal is -(row sum) taken in the stored column order, which the renumbering changes
+        assert np.allclose(a.data[~offd], o.val[~offd], rtol=1e-12, atol=0)      # up-to-900-term row sums, reordered
+        if natural:
+            assert np.array_equal(a.data, o.val)
+        x = np.random.default_rng(0).standard_normal(h.n_nodes)
+        y = h.spmv(x)                                            # takes and returns vectors in file ids
+        yo = o.spmv(x)
+        assert np.abs(y - yo).max() <= 1e-12 * np.abs(yo).max()
+        assert np.abs(h.spmv(np.ones(h.n_nodes))).max() < 1e-13 * np.abs(o.val).max() * 64   # L 1 = 0 up to row round-off
 
 
 # ---------------------------------------------------------------------------------------------------
