@@ -296,6 +296,15 @@ __global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t ro
   blk_row[b] = lo;
 }
 
+__global__ void blk_info_kernel(const int32_t *__restrict__ blk_row, const int32_t *__restrict__ rowptr, int32_t n_blocks,
+                                int4 *__restrict__ info) {
+  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_blocks) {
+    const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
+    info[b] = make_int4(r0, r1, rowptr[r0], rowptr[r1]);
+  }
+}
+
 // Row-block size in non-zeros.  The circuits here are small next to a B200 (ibm01: 0.23 M non-zeros vs
 // 0.3 M resident threads), so the kernels are latency bound: the chunk is sized to spread the matrix
 // over the CTAs resident at once (6 per SM for the SpMV kernel, 8 for the D-value kernel) in ONE wave,
@@ -409,10 +418,19 @@ void assemble_laplacian(eigkl_handle *h) {
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   L.diag_min = dmm[0]; L.diag_max = dmm[1];
   const int64_t nnz_local = (int64_t)rp[1] - rp[0];
-  const int64_t chunk = pick_chunk(h, nnz_local, 6);
+  // which SpMV kernel runs this matrix: the flat kernel (shared-memory staged row blocks, one round of loads
+  // per block; blocks that hold a row too long for the staging buffer fall back to warp-per-row inside it).
+  // Measured warm, flat vs sub-warp: ibm01 5.1 vs 7.3 us, ibm10 10.3 vs 14.4, industry2 10.4 vs 12.4,
+  // synthetic x1 10.3 vs 15.3.  EIGKL_SPMV_MODE = 1 / 2 select the older staged / sub-warp kernels.
+  L.flat = (h->spmv_mode == 3) || (h->spmv_mode == 0);
+  int64_t chunk = pick_chunk(h, nnz_local, L.flat ? 4 : 6);
+  if (L.flat) chunk = std::min<int64_t>(chunk, 1792);     // 2048-product staging buffer minus slack for the last row
   L.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(nnz_local, chunk));
   L.blk_row.alloc((size_t)L.n_blocks + 1);
+  L.blk_info.alloc((size_t)4 * L.n_blocks + 4);
   row_blocks_kernel<<<grid_for(L.n_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, L.row_lo, L.row_hi, chunk, L.n_blocks, L.blk_row.p);
+  blk_info_kernel<<<grid_for(L.n_blocks), TPB, 0, h->stream>>>(L.blk_row.p, L.rowptr.p, L.n_blocks, reinterpret_cast<int4 *>(L.blk_info.p));
+  h->launches++;
   h->launches += 3;
   EIGKL_CUDA(cudaGetLastError());
   L.valid = true;

@@ -163,6 +163,8 @@ struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, dia
   int32_t row_lo = 0, row_hi = 0;
   int32_t n_blocks = 0;
   DBuf<int32_t> blk_row;
+  DBuf<int32_t> blk_info;      // 4 ints per row block: r0, r1, first entry, end entry (the flat SpMV's descriptor)
+  bool flat = false;           // row blocks are sized for / run by spmv_flat_kernel
   DBuf<unsigned long long> diag_minmax;   // [0] = orderable(min L_ii) complemented, [1] = orderable(max L_ii)
   double diag_min = 0, diag_max = 0;      // spectrum bounds: lambda_max <= 2 max L_ii, lambda_2 <= n/(n-1) min L_ii
   bool valid = false;
