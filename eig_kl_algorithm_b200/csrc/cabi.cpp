@@ -129,6 +129,7 @@ int eigkl_create(eigkl_handle **out, const eigkl_opts *opts) {
     h->timer.init();
     h->prof.on = (h->opts.flags & EIGKL_F_PROFILE) != 0;
     if (const char *m = getenv("EIGKL_SPMV_MODE")) h->spmv_mode = atoi(m);
+    if (const char *m = getenv("EIGKL_SPMV_PDL")) h->spmv_pdl = atoi(m);
     h->stats.struct_size = sizeof(eigkl_stats);
     if (h->opts.nranks > 1) comm_init(h);
     *out = h;

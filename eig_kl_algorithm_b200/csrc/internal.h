@@ -242,7 +242,8 @@ struct eigkl_handle {
   eigkl::KlCsr A;
   eigkl::KlState kl;
   eigkl::EigState eig;
-  int spmv_mode = 0;           // EIGKL_SPMV_MODE: 0 auto, 1 stream, 2 vector (tuning aid)
+  int spmv_mode = 0;           // EIGKL_SPMV_MODE: 0 auto (flat), 1 staged, 2 sub-warp, 3 flat (tuning aid)
+  int spmv_pdl = 1;            // EIGKL_SPMV_PDL=0 disables programmatic dependent launch of the SpMV chain
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
   // scratch of the sort / scan primitives

@@ -193,13 +193,18 @@ spmv_flat_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
   __shared__ int32_t long_rows[SPMV_MAX_LONG];
   __shared__ int n_long;
   const int tid = threadIdx.x;
+  // Programmatic dependent launch: the next kernel in the stream may start launching now; everything this
+  // kernel reads before griddepcontrol.wait (block descriptor, row pointers, matrix entries) is constant,
+  // so that prologue overlaps the tail of the previous kernel (whose output x this SpMV gathers).
+  asm volatile("griddepcontrol.launch_dependents;");
   const int4 info = __ldg(blk_info + blockIdx.x);
   const int32_t r0 = info.x, r1 = info.y, e0 = info.z, e1 = info.w;
   if (r0 >= r1) return;
   const int32_t span = e1 - e0, nrows = r1 - r0;
-  const double sc = scale ? __ldg(scale) : 1.0;
-  const SpmvEpilogue ep{xl, z, y, ca * sc, cb * sc, cg, row_offset};
   if (span > FLAT_CAP) {                               // a very long row lives here
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    const double sc = scale ? __ldg(scale) : 1.0;
+    const SpmvEpilogue ep{xl, z, y, ca * sc, cb * sc, cg, row_offset};
     if (v_store)
       for (int32_t r = r0 + tid; r < r1; r += SPMV_THREADS) v_store[r - row_offset] = xl[r - row_offset] * sc;
     rows_subwarp<32>(rowptr, col, val, x, ep, r0, r1, tid, long_rows, &n_long);
@@ -214,6 +219,9 @@ spmv_flat_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
     if (i < span) { a[k] = __ldcs(val + e0 + i); c[k] = __ldcs(col + e0 + i); }
   }
   for (int32_t rr = tid; rr <= nrows; rr += SPMV_THREADS) rp[rr] = rowptr[r0 + rr] - e0;
+  asm volatile("griddepcontrol.wait;" ::: "memory");   // the previous kernel (producer of x, z, *scale) is complete
+  const double sc = scale ? __ldg(scale) : 1.0;
+  const SpmvEpilogue ep{xl, z, y, ca * sc, cb * sc, cg, row_offset};
   double pre0 = 0.0, xs0 = 0.0;
   if (tid < nrows) {
     pre0 = ep.prefetch(r0 + tid);
@@ -252,11 +260,20 @@ void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const d
   if (L.row_hi <= L.row_lo) return;
   h->prof.begin(KC_SPMV, h->stream);
   const bool with_stream = h->spmv_mode == 1 || (h->spmv_mode == 0 && L.nnz < 6 * (int64_t)L.n);
-  if (L.flat)
-    spmv_flat_kernel<<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, xg, xl, z, y,
-                                                                         reinterpret_cast<const int4 *>(L.blk_info.p), scale_inv,
-                                                                         store_scaled, L.row_lo, ca, cb, cg);
-  else if (with_stream)
+  if (L.flat) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)L.n_blocks);
+    cfg.blockDim = dim3(SPMV_THREADS);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = h->spmv_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int4 *info = reinterpret_cast<const int4 *>(L.blk_info.p);
+    const int32_t *rp = L.rowptr.p, *cl = L.col.p;
+    const double *vl = L.val.p;
+    EIGKL_CUDA(cudaLaunchKernelEx(&cfg, spmv_flat_kernel, rp, cl, vl, xg, xl, z, y, info, scale_inv, store_scaled, L.row_lo, ca, cb, cg));
+  } else if (with_stream)
     spmv_adaptive_kernel<true><<<(unsigned)L.n_blocks, SPMV_THREADS, 0, h->stream>>>(L.rowptr.p, L.col.p, L.val.p, xg, xl, z, y, L.blk_row.p,
                                                                                    scale_inv, store_scaled, L.row_lo, h->spmv_mode, ca, cb, cg);
   else
