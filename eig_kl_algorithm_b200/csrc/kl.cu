@@ -31,6 +31,8 @@
 #include <algorithm>
 #include <cmath>
 #include <cstddef>
+#include <cstdio>
+#include <cstdlib>
 
 namespace cg = cooperative_groups;
 
@@ -174,7 +176,7 @@ static void kl_alloc_state(eigkl_handle *h, int32_t n) {
   const int64_t n_tiles = ceil_div(n, KL_TILE);
   k.tile_key.ensure((size_t)(2 * n_tiles + 2 * KL_MAX_CLUSTER + 8));
   k.tile_stamp.ensure((size_t)n_tiles + 1);
-  k.ctrl.ensure(8);
+  k.ctrl.ensure(16);
 }
 
 void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
@@ -477,6 +479,10 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
   }
   __syncthreads();
   uint32_t it_local = sh_iter;
+  // phase clocks of the swap loop (thread 0 only; a handful of clock reads per swap): published in ctrl[8..13]
+  long long tph[6] = {0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define KL_PHASE(i) do { if (tid == 0) { const long long t_ = clock64(); tph[i] += t_ - tprev; tprev = t_; } } while (0)
 
   while (!sh_done) {
     // ---- S1: best pair over the cached tile keys ------------------------------------------------
@@ -513,6 +519,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
     }
     }   // !MULTI
     __syncthreads();
+    KL_PHASE(0);                                     // S1: tile-key reduction
     const unsigned long long b0 = sh_best[0], b1 = sh_best[1];
     if (b0 == 0ull || b1 == 0ull) {                  // no selectable node on one side (cKL.cpp:387-389)
       if (tid == 0) sh_done = 1;
@@ -525,6 +532,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
     const int32_t alo = __ldg(p.rowptr + a), ahi = __ldg(p.rowptr + a + 1);
     const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
     const int32_t da = ahi - alo, items = da + (bhi - blo);
+    KL_PHASE(1);                                     // decode (a, b), their row pointers
     constexpr int WORKERS = KL_LOOP_THREADS / 32 - 1;    // warp 31 of every CTA is the bookkeeper
     const unsigned gworker = cr * WORKERS + warp, total_workers = nc * WORKERS;
     int32_t vkeep[4];
@@ -564,40 +572,46 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
         if (lane == 0) __stcg(p.val + v, nv);
       }
     }
+    KL_PHASE(2);                                     // S3 as seen by warp 0 (its own rows)
     if (nc == 1) __syncthreads(); else cluster.sync();   // one CTA: a block barrier orders the .cg accesses
+    KL_PHASE(3);                                     // wait for the slowest S3 warp / the bookkeeper
     // ---- S4: rescan the tiles that contain a touched node (the bookkeeper takes the tiles of a and b) ----
     const uint32_t stamp = it_local;
-    if (warp == WORKERS) {
-      for (int q = 0; q < 2; ++q) {
-        const int32_t v = q ? b : a;
-        if (cr != 0 || (MULTI && (v < p.own_lo || v >= p.own_hi))) continue;
-        const int32_t tile = v / KL_TILE;
-        unsigned claimed = 0;
-        if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
-        claimed = __shfl_sync(FULL_MASK, claimed, 0);
-        if (claimed) {
-          unsigned long long t0, t1;
-          tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, tile, lane, t0, t1);
-          if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
+    {
+      // Every warp first claims ALL its tiles at once (lane k stamps the tile of the warp's k-th node: one
+      // atomic round trip for the whole batch instead of one per node), then rescans the claimed ones.
+      // The bookkeeper's batch is {a, b}; a worker's batch is the nodes it recomputed in S3.
+      const bool keeper = (warp == WORKERS);
+      const int32_t n_mine = keeper ? ((cr == 0) ? 2 : 0)
+                                    : (items > (int32_t)gworker ? (items - 1 - (int32_t)gworker) / (int32_t)total_workers + 1 : 0);
+      for (int32_t b0i = 0; b0i < n_mine; b0i += 32) {
+        const int32_t kidx = b0i + lane;
+        int32_t tile = -1;
+        if (kidx < n_mine) {
+          int32_t v;
+          if (keeper) v = kidx ? b : a;
+          else {
+            const int32_t it = (int32_t)gworker + kidx * (int32_t)total_workers;
+            v = (kidx < 4) ? vkeep[kidx] : __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
+          }
+          if (!(MULTI && (v < p.own_lo || v >= p.own_hi))) tile = v / KL_TILE;
         }
-      }
-    } else {
-      int kept = 0;
-      for (int32_t it = gworker; it < items; it += total_workers, ++kept) {
-        const int32_t v = (kept < 4) ? vkeep[kept] : __ldg(p.col + (it < da ? alo + it : blo + (it - da)));
-        if (MULTI && (v < p.own_lo || v >= p.own_hi)) continue;
-        const int32_t tile = v / KL_TILE;
-        unsigned claimed = 0;
-        if (lane == 0) claimed = (atomicExch(p.tile_stamp + tile, stamp) != stamp) ? 1u : 0u;
-        claimed = __shfl_sync(FULL_MASK, claimed, 0);
-        if (claimed) {
+        bool claimed = false;
+        if (tile >= 0) claimed = atomicExch(p.tile_stamp + tile, stamp) != stamp;
+        unsigned todo = __ballot_sync(FULL_MASK, claimed);
+        while (todo) {
+          const int src = __ffs(todo) - 1;
+          todo &= todo - 1;
+          const int32_t t = __shfl_sync(FULL_MASK, tile, src);
           unsigned long long t0, t1;
-          tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, tile, lane, t0, t1);
-          if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)tile, t0); __stcg(p.tile_key + 2 * (size_t)tile + 1, t1); }
+          tile_scan(p.state, p.val, p.rank, p.own_lo, p.own_hi, t, lane, t0, t1);
+          if (lane == 0) { __stcg(p.tile_key + 2 * (size_t)t, t0); __stcg(p.tile_key + 2 * (size_t)t + 1, t1); }
         }
       }
     }
+    KL_PHASE(4);                                     // S4 as seen by warp 0
     if (nc == 1) __syncthreads(); else cluster.sync();
+    KL_PHASE(5);                                     // wait for the slowest S4 warp
     if (MULTI) break;                                  // one swap per launch
   }
   if (cr == 0 && tid == 0) {
@@ -606,7 +620,10 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
       p.mctrl->rem0 = sh_rem0; p.mctrl->rem1 = sh_rem1;
     }
     p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1;
+    if (!MULTI)
+      for (int i = 0; i < 6; ++i) p.ctrl[8 + i] = tph[i];
   }
+#undef KL_PHASE
 }
 
 void kl_run(eigkl_handle *h) {
@@ -701,7 +718,7 @@ void kl_run(eigkl_handle *h) {
     }
   }
   h->timer.stop(st);
-  int64_t ctrl[2] = {0, 0};
+  int64_t ctrl[16] = {0};
   EIGKL_CUDA(cudaMemcpyAsync(ctrl, k.ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
   EIGKL_CUDA(cudaStreamSynchronize(st));
   EIGKL_CUDA(cudaGetLastError());
@@ -709,6 +726,12 @@ void kl_run(eigkl_handle *h) {
   EIGKL_REQUIRE(ctrl[1] == 1, EIGKL_E_CUDA, "KL kernel did not complete");
   k.swaps = ctrl[0];
   h->stats.kl_swaps = k.swaps;
+  if (getenv("EIGKL_KL_PHASES") && R == 1 && k.swaps > 0) {
+    static const char *nm[6] = {"S1 reduce", "decode", "S3 own rows", "S3 barrier wait", "S4 own tiles", "S4 barrier wait"};
+    fprintf(stderr, "[eigkl] KL phases, cycles per swap (thread 0):");
+    for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f;", nm[i], (double)ctrl[8 + i] / (double)k.swaps);
+    fprintf(stderr, "\n");
+  }
   h->stats.kl_cluster = nc;
   h->stats.kl_threads = nc * KL_LOOP_THREADS;
 }
