@@ -70,21 +70,31 @@ multidot_kernel(const double *__restrict__ V, size_t ld, int ncols, const double
                 const int *__restrict__ skip_flag) {
   __shared__ double sm[LZ_THREADS / 32][MD_COLS];
   __shared__ bool am_last;
-  if (skip_flag && *skip_flag) return;      // second Gram-Schmidt pass not needed (see update_kernel)
+  // Programmatic dependent launch: the basis columns 0..ncols-2 were written in earlier steps, so they are
+  // loaded while the producer of w (the last SpMV of the filter, or the previous update) is still draining.
+  // The newest column (ncols-1) may come from the immediately preceding SpMV (degree-1 filter): after the wait.
+  asm volatile("griddepcontrol.launch_dependents;");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int c0 = blockIdx.y * MD_COLS;
   const int nc = min(MD_COLS, ncols - c0);
   const unsigned nbx = gridDim.x;
   const int32_t i = (blockIdx.x * LZ_THREADS + tid) * 2;
+  double2 v[MD_COLS];
+  if (i + 1 < n) {
+#pragma unroll
+    for (int g = 0; g < MD_COLS; ++g)
+      if (g < nc && c0 + g != ncols - 1) v[g] = *reinterpret_cast<const double2 *>(V + (size_t)(c0 + g) * ld + i);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (skip_flag && *skip_flag) return;      // second Gram-Schmidt pass not needed (see update_kernel)
   double acc[MD_COLS];
 #pragma unroll
   for (int g = 0; g < MD_COLS; ++g) acc[g] = 0.0;
   if (i + 1 < n) {
     const double2 w2 = *reinterpret_cast<const double2 *>(w + i);
-    double2 v[MD_COLS];
 #pragma unroll
     for (int g = 0; g < MD_COLS; ++g)
-      if (g < nc) v[g] = *reinterpret_cast<const double2 *>(V + (size_t)(c0 + g) * ld + i);
+      if (g < nc && c0 + g == ncols - 1) v[g] = *reinterpret_cast<const double2 *>(V + (size_t)(c0 + g) * ld + i);
 #pragma unroll
     for (int g = 0; g < MD_COLS; ++g)
       if (g < nc) acc[g] = v[g].x * w2.x + v[g].y * w2.y;
@@ -145,15 +155,31 @@ update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__rest
   extern __shared__ double hs[];            // ncols
   __shared__ double sm[8];
   __shared__ bool am_last;
-  if (pass == 2 && *flag) return;           // second pass not needed (uniform for the whole grid)
   const int tid = threadIdx.x;
+  // dependent launch: the first 16 basis columns of the thread's first row (written in earlier steps; the
+  // newest column is never among them once ncols > 16) are fetched while the multidot that produces h drains
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int32_t i0 = blockIdx.x * LZ_THREADS + tid;
+  double vpre[UP_UNROLL];
+  const bool pre_ok = (i0 < n) && (ncols > UP_UNROLL);
+  if (pre_ok) {
+#pragma unroll
+    for (int u = 0; u < UP_UNROLL; ++u) vpre[u] = V[(size_t)u * ld + i0];
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (pass == 2 && *flag) return;           // second pass not needed (uniform for the whole grid)
   for (int c = tid; c < ncols; c += LZ_THREADS) hs[c] = h[c];
   __syncthreads();
   double nrm = 0.0;
-  for (int32_t i = blockIdx.x * LZ_THREADS + tid; i < n; i += gridDim.x * LZ_THREADS) {
+  for (int32_t i = i0; i < n; i += gridDim.x * LZ_THREADS) {
     double s = w[i];
     const double *vp = V + i;
     int c = 0;
+    if (pre_ok && i == i0) {
+#pragma unroll
+      for (int u = 0; u < UP_UNROLL; ++u) s -= vpre[u] * hs[u];
+      c = UP_UNROLL;
+    }
     for (; c + UP_UNROLL <= ncols; c += UP_UNROLL) {
       double v[UP_UNROLL];
 #pragma unroll
@@ -312,8 +338,16 @@ void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, doub
   if (c.nl > 0) {
     dim3 grid((unsigned)c.gx_md, (unsigned)ceil_div(ncols, MD_COLS));
     c.h->prof.begin(KC_MULTIDOT, c.h->stream);
-    multidot_kernel<<<grid, LZ_THREADS, 0, c.h->stream>>>(V, c.ld, ncols, w, c.nl, e.partial.p, e.counters.p + 8, h_out,
-                                                        pass == 2 ? e.flag.p : nullptr);
+    {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = grid; cfg.blockDim = dim3(LZ_THREADS); cfg.stream = c.h->stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = c.h->spmv_pdl ? 1 : 0;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      const int *sf = pass == 2 ? e.flag.p : nullptr;
+      EIGKL_CUDA(cudaLaunchKernelEx(&cfg, multidot_kernel, V, c.ld, ncols, w, c.nl, e.partial.p, e.counters.p + 8, h_out, sf));
+    }
     c.h->prof.end(c.h->stream);
     c.h->launches++;
     c.h->stats.bytes_multidot_total += c.h->prof.on ? ((double)ncols * c.nl * 8.0 + (double)c.nl * 8.0) : 0.0;
@@ -327,9 +361,17 @@ void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double
   const int single = c.R == 1 ? 1 : 0;
   if (c.nl > 0) {
     c.h->prof.begin(KC_UPDATE, c.h->stream);
-    update_kernel<<<(unsigned)c.gx_up, LZ_THREADS, (size_t)ncols * sizeof(double), c.h->stream>>>(
-        V, c.ld, ncols, w, c.nl, hcoef, e.partial.p, e.counters.p + 1, e.scal.p, e.beta.p, e.alpha.p, h_prev, j, pass, single,
-        c.eta2, e.flag.p);
+    {
+      cudaLaunchConfig_t cfg{};
+      cfg.gridDim = dim3((unsigned)c.gx_up); cfg.blockDim = dim3(LZ_THREADS); cfg.stream = c.h->stream;
+      cfg.dynamicSmemBytes = (size_t)ncols * sizeof(double);
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      attr[0].val.programmaticStreamSerializationAllowed = c.h->spmv_pdl ? 1 : 0;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      EIGKL_CUDA(cudaLaunchKernelEx(&cfg, update_kernel, V, c.ld, ncols, w, c.nl, hcoef, e.partial.p, e.counters.p + 1, e.scal.p,
+                                    e.beta.p, e.alpha.p, h_prev, j, pass, single, c.eta2, e.flag.p));
+    }
     c.h->prof.end(c.h->stream);
     c.h->launches++;
     c.h->stats.bytes_update_total += c.h->prof.on ? ((double)ncols * c.nl * 8.0 + (double)c.nl * 16.0) : 0.0;
@@ -528,6 +570,8 @@ void fiedler_solve(eigkl_handle *h) {
   // Rayleigh-Ritz on L over the two Ritz vectors; returns the true residual of the Fiedler pair
   double lam1 = 0, lam2 = 0;
   auto extract = [&](int jj) -> double {
+    // no dependent launches here: these kernels read columns that the kernel just before them wrote
+    struct PdlOff { int &f; int saved; PdlOff(int &x) : f(x), saved(x) { f = 0; } ~PdlOff() { f = saved; } } pdl_off(h->spmv_pdl);
     double *V = e.V[bank].p, *Vn = e.V[bank ^ 1].p;           // Vn columns 0,1 = X ; 2,3 = L X ; 4,5 = scratch
     double *scratch = Vn + (size_t)4 * c.ld;
     // the live Lanczos state (w buffers, 1/beta in scal[1]) must survive a rejected extraction
