@@ -280,18 +280,20 @@ __global__ void lap_diag_kernel(const int32_t *__restrict__ rowptr, const int32_
 __global__ void diag_decode_kernel(const unsigned long long *__restrict__ minmax, double *__restrict__ out) {
   if (threadIdx.x == 0 && blockIdx.x == 0) { out[0] = double_from_orderable(~minmax[0]); out[1] = double_from_orderable(minmax[1]); }
 }
-// blk_row[b] = first row r in [row_lo, row_hi] with rowptr[r] >= rowptr[row_lo] + b*chunk
+// blk_row[b] = first row r in [row_lo, row_hi] with cost(r) >= b*chunk, where
+// cost(r) = rowptr[r] - rowptr[row_lo] + row_weight * (r - row_lo)   (non-zeros, plus a per-row charge)
 // (b in [0, n_blocks]; blk_row[n_blocks] = row_hi)
 __global__ void row_blocks_kernel(const int32_t *__restrict__ rowptr, int32_t row_lo, int32_t row_hi, int64_t chunk,
-                                  int32_t n_blocks, int32_t *__restrict__ blk_row) {
+                                  int32_t n_blocks, int32_t *__restrict__ blk_row, int64_t row_weight = 0) {
   int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b > n_blocks) return;
   if (b == n_blocks) { blk_row[b] = row_hi; return; }
-  const int64_t x = (int64_t)rowptr[row_lo] + (int64_t)b * chunk;
+  const int64_t base = (int64_t)rowptr[row_lo];
+  const int64_t x = (int64_t)b * chunk;
   int32_t lo = row_lo, hi = row_hi;
   while (lo < hi) {
     int32_t mid = (lo + hi) >> 1;
-    if ((int64_t)rowptr[mid] < x) lo = mid + 1; else hi = mid;
+    if ((int64_t)rowptr[mid] - base + row_weight * (int64_t)(mid - row_lo) < x) lo = mid + 1; else hi = mid;
   }
   blk_row[b] = lo;
 }
@@ -302,6 +304,16 @@ __global__ void blk_info_kernel(const int32_t *__restrict__ blk_row, const int32
   if (b < n_blocks) {
     const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
     info[b] = make_int4(r0, r1, rowptr[r0], rowptr[r1]);
+  }
+}
+
+// res_check[0] = longest span, [1] = most rows over the resident row blocks
+__global__ void blk_check_kernel(const int4 *__restrict__ info, int32_t n_blocks, int32_t *__restrict__ out) {
+  int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < n_blocks) {
+    const int4 i = info[b];
+    atomicMax(out, i.w - i.z);
+    atomicMax(out + 1, i.y - i.x);
   }
 }
 
@@ -380,6 +392,16 @@ static void build_node_order(eigkl_handle *h) {
   o.valid = true;
 }
 
+// row blocks of the resident filter: cost = non-zeros + rows, cut every `chunk`
+void resident_row_blocks(eigkl_handle *h, int64_t chunk) {
+  auto &L = h->L;
+  row_blocks_kernel<<<grid_for(L.res_blocks + 1), TPB, 0, h->stream>>>(L.rowptr.p, 0, L.n, chunk, L.res_blocks, L.res_row.p, 1);
+  blk_info_kernel<<<grid_for(L.res_blocks), TPB, 0, h->stream>>>(L.res_row.p, L.rowptr.p, L.res_blocks, reinterpret_cast<int4 *>(L.res_info.p));
+  blk_check_kernel<<<grid_for(L.res_blocks), TPB, 0, h->stream>>>(reinterpret_cast<const int4 *>(L.res_info.p), L.res_blocks, L.res_check.p);
+  EIGKL_CUDA(cudaGetLastError());
+  h->launches += 3;
+}
+
 void assemble_laplacian(eigkl_handle *h) {
   build_node_order(h);
   auto &ue = h->order.active ? h->ueL : h->ue;
@@ -415,8 +437,10 @@ void assemble_laplacian(eigkl_handle *h) {
   int32_t rp[2] = {0, 0};
   EIGKL_CUDA(cudaMemcpyAsync(&rp[0], L.rowptr.p + L.row_lo, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaMemcpyAsync(&rp[1], L.rowptr.p + L.row_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+  cheb_resident_plan(h);     // resident polynomial filter (spmv.cu): plan enqueued, checked after the sync
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   L.diag_min = dmm[0]; L.diag_max = dmm[1];
+  cheb_resident_plan_finish(h);
   const int64_t nnz_local = (int64_t)rp[1] - rp[0];
   // which SpMV kernel runs this matrix: the flat kernel (shared-memory staged row blocks, one round of loads
   // per block; blocks that hold a row too long for the staging buffer fall back to warp-per-row inside it).

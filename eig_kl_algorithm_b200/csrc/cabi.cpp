@@ -130,6 +130,7 @@ int eigkl_create(eigkl_handle **out, const eigkl_opts *opts) {
     h->prof.on = (h->opts.flags & EIGKL_F_PROFILE) != 0;
     if (const char *m = getenv("EIGKL_SPMV_MODE")) h->spmv_mode = atoi(m);
     if (const char *m = getenv("EIGKL_SPMV_PDL")) h->spmv_pdl = atoi(m);
+    if (const char *m = getenv("EIGKL_SPMV_RESIDENT")) h->spmv_resident = atoi(m);
     h->stats.struct_size = sizeof(eigkl_stats);
     if (h->opts.nranks > 1) comm_init(h);
     *out = h;
@@ -258,6 +259,7 @@ int eigkl_fiedler(eigkl_handle *h, double *lambda2, double *vec) {
     EIGKL_CUDA(cudaEventElapsedTime(&ms, a, b));
     cudaEventDestroy(a); cudaEventDestroy(b);
     h->stats.ms_fiedler = ms;
+    spmv_resident_print_phases();
     if (lambda2) *lambda2 = h->eig.lambda2;
     if (vec) {
       EIGKL_CUDA(cudaMemcpyAsync(vec, h->eig.fiedler.p, (size_t)h->eig.n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

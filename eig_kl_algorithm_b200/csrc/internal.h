@@ -165,6 +165,20 @@ struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, dia
   DBuf<int32_t> blk_row;
   DBuf<int32_t> blk_info;      // 4 ints per row block: r0, r1, first entry, end entry (the flat SpMV's descriptor)
   bool flat = false;           // row blocks are sized for / run by spmv_flat_kernel
+  // resident polynomial filter (single rank): at most one row block per SM, small enough that its matrix
+  // entries stay in registers / shared memory across all SpMVs of one filter application
+  DBuf<int32_t> res_info;      // 4 ints per resident block, as blk_info
+  DBuf<int32_t> res_row;       // first row of each resident block
+  DBuf<int32_t> res_check;     // [0] = longest block span, [1] = most rows in a block, [2] = largest halo
+  int32_t res_check_host[4] = {0, 0, 0, 0};
+  DBuf<uint16_t> res_src;      // per entry: index into the owning CTA's x cache, bit 15 = row start
+  DBuf<int32_t> res_halo_ids, res_halo_cnt;   // per block: sorted distinct columns outside its rows
+  int64_t res_chunk = 0;
+  int res_k = 0;               // entries per thread of the resident kernel (4, 8 or 16)
+  DBuf<unsigned long long> res_ll;   // halo exchange buffer: 2 slots x n x {lo, tag, hi, tag}
+  uint32_t res_tag = 0;        // tags handed out so far (monotonic; y_k of a launch carries res_tag + k)
+  int32_t res_blocks = 0;
+  bool res_ok = false;
   DBuf<unsigned long long> diag_minmax;   // [0] = orderable(min L_ii) complemented, [1] = orderable(max L_ii)
   double diag_min = 0, diag_max = 0;      // spectrum bounds: lambda_max <= 2 max L_ii, lambda_2 <= n/(n-1) min L_ii
   bool valid = false;
@@ -244,6 +258,7 @@ struct eigkl_handle {
   eigkl::EigState eig;
   int spmv_mode = 0;           // EIGKL_SPMV_MODE: 0 auto (flat), 1 staged, 2 sub-warp, 3 flat (tuning aid)
   int spmv_pdl = 1;            // EIGKL_SPMV_PDL=0 disables programmatic dependent launch of the SpMV chain
+  int spmv_resident = 1;       // EIGKL_SPMV_RESIDENT=0: one launch per SpMV even when the matrix fits on chip
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
   // scratch of the sort / scan primitives
@@ -279,6 +294,14 @@ void assemble_kl_graph(eigkl_handle *h);
 // ---- EIG (spmv.cu, lanczos.cu, eig_solver.cpp) ------------------------------------------------------
 void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scale_inv /*device or null*/,
                  double *store_scaled /*or null*/);
+// the whole Chebyshev recurrence (deg SpMVs) as ONE cooperative launch; out_idx[k] = index into w[] of y_{k+1}
+bool cheb_resident_usable(const eigkl_handle *h);
+void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *scale, double *v_store, double *const w[3],
+                          const unsigned char *out_idx, int deg, double fc, double fe);
+void spmv_resident_print_phases();
+void cheb_resident_plan(eigkl_handle *h);          // enqueue (no sync)
+void cheb_resident_plan_finish(eigkl_handle *h);   // after the stream has been synchronised
+void resident_row_blocks(eigkl_handle *h, int64_t chunk);   // assemble.cu
 void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const double *z, double *y, const double *scale_inv,
                     double *store_scaled, double ca, double cb, double cg);
 void fiedler_solve(eigkl_handle *h);

@@ -502,12 +502,30 @@ void fiedler_solve(eigkl_handle *h) {
 
   // w = B x:  d SpMVs, recurrence fused.  x is either an un-normalised buffer (scale = 1/beta, v_j stored)
   // or an already normalised basis column (after a restart).  Returns the index of the buffer holding w.
+  const bool resident = cheb_resident_usable(h) && deg >= 2 && deg <= 64;
   auto apply_filter = [&](const double *x_in, const double *scale, double *v_store, const double *v_norm, int avoid) -> int {
     // profiling brackets the whole chain of `deg` back-to-back SpMVs with ONE event pair (single rank), so the
     // ~2 us an event pair costs is not charged to every 15 us launch
     const bool group = h->prof.on && c.R == 1;
-    if (group) { h->prof.begin(KC_SPMV, st, deg); h->prof.suppress++; }
     int o1 = (avoid + 1) % 3;
+    if (resident) {
+      // the whole recurrence in one cooperative launch (spmv.cu); same buffer rotation as below
+      unsigned char out_idx[64];
+      out_idx[0] = (unsigned char)o1;
+      int p1 = o1, p2 = -1;                    // p2 = -1: y_0 is not one of the three work buffers
+      for (int kk = 2; kk <= deg; ++kk) {
+        int o = 0;
+        while (o == p1 || o == p2) ++o;
+        out_idx[kk - 1] = (unsigned char)o;
+        p2 = p1; p1 = o;
+      }
+      double *wp[3] = {e.w[0].p, e.w[1].p, e.w[2].p};
+      h->prof.begin(KC_SPMV, st, deg);
+      cheb_resident_launch(h, x_in, scale, v_store, wp, out_idx, deg, fc, fe);
+      h->prof.end(st);
+      return p1;
+    }
+    if (group) { h->prof.begin(KC_SPMV, st, deg); h->prof.suppress++; }
     // y1 = s * (c x - L x) / e
     spmv_launch_ex(h, gathered(c, x_in), x_in, nullptr, e.w[o1].p, scale, v_store, -1.0 / fe, fc / fe, 0.0);
     const double *prev2 = v_norm;            // normalised v_j (= T_0 x)

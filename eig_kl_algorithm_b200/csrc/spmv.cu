@@ -18,6 +18,9 @@
 // the normalisation v_j = w/beta are applied by the SpMV itself (no separate axpy/scale kernels).
 // Bound: HBM (or L2 when the matrix fits the 126 MB L2): nnz*12 + n*20 bytes per launch.
 #include "internal.h"
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include "device_utils.cuh"
 
 namespace eigkl {
@@ -248,6 +251,443 @@ spmv_flat_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
       if (v_store) v_store[r - row_offset] = xl[r - row_offset] * sc;
     }
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// Resident polynomial filter: the d SpMVs of one Chebyshev filter application as ONE cooperative launch.
+//
+// On the shipped circuits a SpMV launch is ~8 us of which the bytes explain ~3: the rest is launch/drain and
+// dependent round trips, paid d = 16 times per Lanczos step.  A circuit's Laplacian (ibm10: 1.5 M entries,
+// 18 MB) does not fit one SM but it does fit the CHIP: 148 SMs x (256 KB registers + 227 KB shared memory).
+// So: one CTA per SM, each owning one row block for the whole recurrence,
+//   * the block's values in registers (K consecutive entries per thread) with their 15-bit source index
+//     and a row-start bit packed two to a register;
+//   * x as this CTA needs it in shared memory: its own rows of y_{k-1} (it produced them) followed by the
+//     block's HALO, the distinct columns outside its row range.  The halo list is built once per matrix
+//     (cheb_resident_plan); per SpMV a CTA loads each halo value ONCE from L2 instead of once per entry
+//     (the first-net node order makes a block reference ~0.2 distinct remote values per entry);
+//   * its own rows of y_{k-2} in shared memory, so the recurrence's epilogue reads no global memory.
+// A thread adds its K products in registers; rows that cross threads are finished by a segmented scan of
+// the threads' open sums (five shuffle steps per warp, one shared-memory hop across warps), so the work
+// per SpMV is the same for every thread whatever the row lengths are.  The SpMVs are separated by a grid
+// barrier (release-add + acquire-poll on one counter) instead of a kernel boundary.  x is re-written inside
+// the kernel, so the halo is read with ordinary coherent loads (no ld.global.nc); the acquire at the
+// barrier invalidates L1.
+// Not used when the matrix does not fit (cheb_resident_plan decides) or with more than one rank (the halo
+// exchange between SpMVs is a NCCL call): those take one spmv_flat_kernel launch per SpMV.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RES_THREADS = 768;
+constexpr int RES_WARPS = RES_THREADS / 32;
+constexpr int RES_KMAX = 16;
+constexpr int RES_CAP = RES_THREADS * RES_KMAX;       // 12288 entry slots per CTA; a block's span is <= RES_CAP - 1
+constexpr int RES_MAXROWS = RES_CAP / 2;              // the builder charges a row like one more entry, so this always holds
+constexpr int RES_MAXHALO = 6144;
+constexpr int RES_STAGE = RES_CAP + RES_THREADS + 8;   // padded staging of the prologue
+static_assert(RES_MAXROWS + RES_MAXHALO <= 32767, "source index must fit 15 bits");
+static_assert(RES_STAGE <= RES_MAXROWS + RES_MAXHALO + RES_MAXROWS, "value staging aliases the x cache and the y_{k-2} rows");
+static_assert(RES_STAGE * 2 <= RES_MAXROWS * 8, "index staging aliases the row sums");
+constexpr size_t RES_SMEM = (size_t)(RES_MAXROWS + RES_MAXHALO) * 8 + 2 * (size_t)RES_MAXROWS * 8 + (size_t)RES_MAXHALO * 4 +
+                            (size_t)RES_WARPS * 16;
+constexpr int PLAN_THREADS = 1024;
+constexpr int32_t PLAN_MAX_N = 800000;                // bitmap + prefix of the plan kernel: n/4 bytes of shared memory
+
+struct ResidentArgs {
+  const double *val;
+  const uint16_t *src;          // per entry: index into the CTA's x cache | 0x8000 at a row start
+  const int4 *info;
+  const int32_t *halo_ids, *halo_cnt;
+  const double *x_in, *scale;
+  double *v_store;
+  double *w[3];
+  uint4 *ll;                    // two slots of n {lo, tag, hi, tag} words: y_k of every row, published for the halos
+  uint32_t tag_base;            // y_k of this launch carries tag tag_base + k
+  int32_t n;
+  int deg;
+  double fc, fe;
+  int phases;
+  unsigned char out_idx[64];
+};
+
+// Halo exchange in the style of NCCL's LL protocol: a value travels as two 8-byte words {low half, tag},
+// {high half, tag}; 8-byte stores are single-copy atomic, so a reader that sees both tags equal to the one it
+// waits for has the value, without any fence or barrier.  Two slots (tag parity) are enough: L is symmetric,
+// so a CTA can only publish y_{k+1} after every CTA that reads its rows has published y_k, i.e. has already
+// consumed its y_{k-1}, the value being overwritten.
+__device__ __forceinline__ void ll_store(uint4 *p, double v, uint32_t tag) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)__double2loint(v)), "r"(tag),
+               "r"((uint32_t)__double2hiint(v)), "r"(tag)
+               : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4 *p) {
+  uint4 v;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  return v;
+}
+
+// per-phase clocks of CTA 0 (EIGKL_RES_PHASES=1 prints them after the solve): halo, products, row sums, barrier
+__device__ unsigned long long res_phase_clk[5];
+#define RES_CLK(slot, t0)                                                         \
+  if (A.phases && blockIdx.x == 0 && tid == 0) {                                  \
+    const long long t1 = clock64();                                               \
+    res_phase_clk[slot] += (unsigned long long)(t1 - t0);                         \
+    t0 = t1;                                                                      \
+  }
+
+// One CTA per resident block, once per matrix: the block's halo (sorted distinct remote columns) and, per
+// entry, where its x value will sit in the CTA's shared-memory x cache (own rows first, then the halo).
+__global__ void __launch_bounds__(PLAN_THREADS)
+res_plan_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, const int4 *__restrict__ info, int32_t n,
+                uint16_t *__restrict__ src, int32_t *__restrict__ halo_ids, int32_t *__restrict__ halo_cnt,
+                int32_t *__restrict__ check) {
+  extern __shared__ uint32_t plan_sm[];
+  const int32_t W = (n + 31) >> 5;
+  uint32_t *bitmap = plan_sm, *prefix = plan_sm + W, *wsum = prefix + W;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int4 bi = info[blockIdx.x];
+  const int32_t r0 = bi.x, r1 = bi.y, e0 = bi.z, span = bi.w - bi.z, nrows = bi.y - bi.x;
+  for (int32_t w = tid; w < W; w += PLAN_THREADS) bitmap[w] = 0u;
+  __syncthreads();
+  for (int32_t i = tid; i < span; i += PLAN_THREADS) {
+    const int32_t c = col[e0 + i];
+    if (c < r0 || c >= r1) atomicOr(&bitmap[c >> 5], 1u << (c & 31));
+  }
+  __syncthreads();
+  const int32_t chunk = (W + PLAN_THREADS - 1) / PLAN_THREADS;
+  const int32_t w0 = min(W, tid * chunk), w1 = min(W, w0 + chunk);
+  uint32_t mine = 0;
+  for (int32_t w = w0; w < w1; ++w) mine += __popc(bitmap[w]);
+  uint32_t inc = mine;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const uint32_t t = __shfl_up_sync(FULL_MASK, inc, d);
+    if (lane >= d) inc += t;
+  }
+  if (lane == 31) wsum[warp] = inc;
+  __syncthreads();
+  uint32_t before = 0;
+  for (int q = 0; q < warp; ++q) before += wsum[q];
+  uint32_t run = before + inc - mine;
+  for (int32_t w = w0; w < w1; ++w) {
+    prefix[w] = run;
+    uint32_t bits = bitmap[w];
+    while (bits) {
+      const int b = __ffs(bits) - 1;
+      if (run < (uint32_t)RES_MAXHALO) halo_ids[(size_t)blockIdx.x * RES_MAXHALO + run] = (w << 5) + b;
+      ++run;
+      bits &= bits - 1;
+    }
+  }
+  if (tid == PLAN_THREADS - 1) {
+    halo_cnt[blockIdx.x] = (int32_t)run;
+    atomicMax(check + 2, (int32_t)run);
+  }
+  __syncthreads();
+  for (int32_t i = tid; i < span; i += PLAN_THREADS) {
+    const int32_t c = col[e0 + i];
+    uint32_t idx;
+    if (c >= r0 && c < r1) idx = (uint32_t)(c - r0);
+    else idx = (uint32_t)nrows + prefix[c >> 5] + __popc(bitmap[c >> 5] & ((1u << (c & 31)) - 1u));
+    src[e0 + i] = (uint16_t)(idx & 0x7FFFu);
+  }
+  __syncthreads();
+  for (int32_t rr = tid; rr < nrows; rr += PLAN_THREADS) src[rowptr[r0 + rr]] |= (uint16_t)0x8000u;
+}
+
+template <int K, int T>
+__global__ void __launch_bounds__(T, 1) cheb_resident_kernel(const ResidentArgs A) {
+  extern __shared__ __align__(16) unsigned char res_smem[];
+  double *xc = reinterpret_cast<double *>(res_smem);              // x cache: own rows of y_{k-1}, then the halo
+  double *zc = xc + RES_MAXROWS + RES_MAXHALO;                    // own rows of y_{k-2}
+  double *rsum = zc + RES_MAXROWS;                                // (L y_{k-1}) of the own rows, as the threads finish them
+  double *wout = rsum + RES_MAXROWS;                              // per warp: sum of the warp's open segment
+  int32_t *wflag = reinterpret_cast<int32_t *>(wout + (T / 32)); // per warp: a row starts inside the warp / start count
+  int32_t *hid = wflag + 2 * (T / 32);                           // halo column ids
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int4 info = A.info[blockIdx.x];
+  const int32_t r0 = info.x, e0 = info.z;
+  const int32_t nrows = info.y - info.x, span = info.w - info.z;
+  const int32_t H = A.halo_cnt[blockIdx.x];
+  // ---- prologue: the block's entries, coalesced into a padded staging area, then K consecutive per thread ----
+  {
+    double *stg_a = xc;
+    uint16_t *stg_s = reinterpret_cast<uint16_t *>(rsum);
+    for (int32_t i = tid; i < T * K; i += T) {
+      double v = 0.0;
+      uint16_t q = (i == span) ? (uint16_t)0x8000u : (uint16_t)0;  // sentinel: the row after the last one starts here
+      if (i < span) { v = __ldcs(A.val + e0 + i); q = __ldcs(A.src + e0 + i); }
+      const int32_t pos = i + i / K;
+      stg_a[pos] = v;
+      stg_s[pos] = q;
+    }
+    const int32_t *hsrc = A.halo_ids + (size_t)blockIdx.x * RES_MAXHALO;
+    for (int32_t j = tid; j < H; j += T) hid[j] = hsrc[j];
+  }
+  __syncthreads();
+  double a[K];
+  uint32_t sp[K / 2];                                             // two 16-bit source words per register
+  uint32_t flags = 0u;
+#pragma unroll
+  for (int k = 0; k < K; ++k) {
+    const int32_t pos = tid * (K + 1) + k;
+    a[k] = xc[pos];
+    const uint32_t q = reinterpret_cast<const uint16_t *>(rsum)[pos];
+    if (k & 1) sp[k / 2] |= q << 16; else sp[k / 2] = q;
+    flags |= (q >> 15) << k;
+  }
+  // first row that starts at or after this thread's entries = number of row starts before them
+  int32_t first_row;
+  {
+    const int cnt = __popc(flags);
+    int inc = cnt;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int t = __shfl_up_sync(FULL_MASK, inc, d);
+      if (lane >= d) inc += t;
+    }
+    if (lane == 31) wflag[(T / 32) + warp] = inc;
+    __syncthreads();                                              // also: the staging area has been consumed
+    int before = 0;
+    for (int q = 0; q < warp; ++q) before += wflag[(T / 32) + q];
+    first_row = before + inc - cnt;
+  }
+  const double sc = A.scale ? *A.scale : 1.0;
+  for (int32_t rr = tid; rr < nrows; rr += T) {
+    const double y0 = sc * A.x_in[r0 + rr];                       // T_0 x = the normalised vector
+    xc[rr] = y0;
+    zc[rr] = 0.0;
+    if (A.v_store) A.v_store[r0 + rr] = y0;
+  }
+  const unsigned wm = __ballot_sync(FULL_MASK, flags != 0u);      // lanes of this warp in which a row starts
+  const unsigned below_eq = wm & ((2u << lane) - 1u), below = wm & ((1u << lane) - 1u);
+  const int seg = below_eq ? 31 - __clz(below_eq) : 0;            // first lane of this lane's scan segment
+  if (lane == 0) wflag[warp] = wm != 0u;
+  double ca = -1.0 / A.fe, cb = A.fc / A.fe, cg = 0.0;            // y1 = (c y0 - L y0) / e
+  double *yout = A.w[A.out_idx[A.deg - 1]];
+  constexpr int HU = (K == 16) ? 2 : 4;                             // halo values in flight per thread (registers are tight at K = 16)
+  long long tclk = clock64();
+  for (int kk = 1; kk <= A.deg; ++kk) {
+    if (kk == 1) {
+      for (int32_t j0 = tid; j0 < H; j0 += T * HU) {
+        double v[HU];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          const int32_t j = j0 + u * T;
+          v[u] = j < H ? A.x_in[hid[j]] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          const int32_t j = j0 + u * T;
+          if (j < H) xc[nrows + j] = sc * v[u];
+        }
+      }
+    } else {
+      const uint32_t tag = A.tag_base + (uint32_t)(kk - 1);       // wait for y_{kk-1} of the rows in the halo
+      const uint4 *src = A.ll + (size_t)(tag & 1u) * (size_t)A.n;
+      for (int32_t j0 = tid; j0 < H; j0 += T * HU) {
+        uint4 v[HU];
+        const uint4 *ptr[HU];
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          const int32_t j = j0 + u * T;
+          ptr[u] = j < H ? src + hid[j] : nullptr;
+        }
+        bool ok;
+        do {
+          ok = true;
+#pragma unroll
+          for (int u = 0; u < HU; ++u)
+            if (ptr[u]) v[u] = ll_load(ptr[u]);
+#pragma unroll
+          for (int u = 0; u < HU; ++u)
+            if (ptr[u]) ok = ok && v[u].y == tag && v[u].w == tag;
+        } while (!ok);
+#pragma unroll
+        for (int u = 0; u < HU; ++u) {
+          const int32_t j = j0 + u * T;
+          if (j < H) xc[nrows + j] = __hiloint2double((int)v[u].z, (int)v[u].x);
+        }
+      }
+    }
+    __syncthreads();
+    RES_CLK(0, tclk);
+    double run = 0.0, head = 0.0;
+    int j = 0;
+    constexpr int XB = K >= 8 ? 8 : K;                            // x values in flight per thread
+#pragma unroll
+    for (int k0 = 0; k0 < K; k0 += XB) {
+      double xv[XB];
+#pragma unroll
+      for (int u = 0; u < XB; ++u) {                              // all loads of the batch before any store: the
+        const int k = k0 + u;                                     // compiler cannot prove rsum[] and xc[] apart
+        const uint32_t q = (k & 1) ? (sp[k / 2] >> 16) : (sp[k / 2] & 0xFFFFu);
+        xv[u] = xc[q & 0x7FFFu];
+      }
+#pragma unroll
+      for (int u = 0; u < XB; ++u) {
+        const int k = k0 + u;
+        if ((flags >> k) & 1u) {
+          if (j == 0) head = run;
+          else rsum[first_row + j - 1] = run;                     // a row that lies entirely inside this thread
+          run = 0.0;
+          ++j;
+        }
+        run = fma(a[k], xv[u], run);
+      }
+    }
+    // segmented inclusive scan of the open sums: inc = sum of `run` over [segment start, lane]
+    double inc = run;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const double t = __shfl_up_sync(FULL_MASK, inc, d);
+      if (lane - d >= seg) inc += t;
+    }
+    if (lane == 31) wout[warp] = inc;
+    double cin = __shfl_up_sync(FULL_MASK, inc, 1);
+    if (lane == 0) cin = 0.0;
+    __syncthreads();
+    RES_CLK(1, tclk);
+    if (flags != 0u && first_row >= 1) {
+      if (below == 0u) {                                          // the row began in an earlier warp
+        for (int wq = warp - 1; wq >= 0; --wq) {
+          cin += wout[wq];
+          if (wflag[wq]) break;
+        }
+      }
+      rsum[first_row - 1] = cin + head;
+    }
+    __syncthreads();
+    const uint32_t tag_out = A.tag_base + (uint32_t)kk;
+    uint4 *dst = A.ll + (size_t)(tag_out & 1u) * (size_t)A.n + r0;
+    for (int32_t rr = tid; rr < nrows; rr += T) {       // y_k = ca L y_{k-1} + cb y_{k-1} + cg y_{k-2}
+      const double xo = xc[rr];
+      const double yn = ca * rsum[rr] + cb * xo + cg * zc[rr];
+      if (kk < A.deg) ll_store(dst + rr, yn, tag_out);            // intermediate vectors exist only for the halos
+      else yout[r0 + rr] = yn;
+      zc[rr] = xo;
+      xc[rr] = yn;
+    }
+    RES_CLK(2, tclk);
+    if (A.phases && blockIdx.x == 0 && tid == 0) res_phase_clk[4] += 1;
+    ca = -2.0 / A.fe; cb = 2.0 * A.fc / A.fe; cg = -1.0;
+  }
+}
+
+void spmv_resident_print_phases() {
+  if (!getenv("EIGKL_RES_PHASES")) return;
+  unsigned long long c[5] = {0, 0, 0, 0, 0};
+  if (cudaMemcpyFromSymbol(c, res_phase_clk, sizeof(c)) != cudaSuccess || c[4] == 0) return;
+  fprintf(stderr, "resident filter, CTA 0, cycles per SpMV: halo wait+load %.0f  products+scan %.0f  rows %.0f  (%llu SpMVs)\n",
+          (double)c[0] / c[4], (double)c[1] / c[4], (double)c[2] / c[4], c[4]);
+  unsigned long long z[5] = {0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(res_phase_clk, z, sizeof(z));
+}
+
+// Decides whether this matrix runs resident and builds its plan (row blocks, halo lists, source indices).
+// Called by assemble_laplacian before its one host synchronisation; cheb_resident_plan_finish reads the
+// checks back after it.
+void cheb_resident_plan(eigkl_handle *h) {
+  auto &L = h->L;
+  const int32_t n = L.n;
+  L.res_ok = false;
+  L.res_blocks = 0;
+  L.res_k = 0;
+  // a row is charged like one more entry, so that a block never holds more rows than half its entry capacity
+  const int64_t cost = L.nnz + (int64_t)n;
+  if (h->opts.nranks != 1 || !h->spmv_resident || n > PLAN_MAX_N || cost > (int64_t)(RES_CAP - 1) * h->sm_count) return;
+  int64_t min_chunk = 1024;
+  if (const char *ev = getenv("EIGKL_RES_CHUNK")) min_chunk = std::max<int64_t>(64, atoll(ev));   // tuning aid
+  int64_t chunk = std::max<int64_t>(min_chunk, ceil_div(cost, (int64_t)h->sm_count));
+  chunk = ceil_div(chunk, 32) * 32;
+  L.res_blocks = (int32_t)std::max<int64_t>(1, ceil_div(cost, chunk));
+  L.res_chunk = chunk;
+  L.res_info.alloc((size_t)4 * L.res_blocks + 4);
+  L.res_row.alloc((size_t)L.res_blocks + 1);
+  L.res_check.alloc(4);
+  L.res_ll.alloc((size_t)4 * n + 8);                // 2 slots x n x 16 bytes
+  L.res_src.alloc((size_t)L.nnz + 8);
+  L.res_halo_ids.alloc((size_t)L.res_blocks * RES_MAXHALO);
+  L.res_halo_cnt.alloc((size_t)L.res_blocks);
+  EIGKL_CUDA(cudaMemsetAsync(L.res_check.p, 0, 4 * sizeof(int32_t), h->stream));
+  EIGKL_CUDA(cudaMemsetAsync(L.res_ll.p, 0, (size_t)4 * n * sizeof(unsigned long long), h->stream));
+  L.res_tag = 0;
+  resident_row_blocks(h, chunk);                                   // assemble.cu: res_row, res_info, res_check[0..1]
+  static bool configured = false;
+  const size_t plan_smem = ((size_t)2 * ((n + 31) / 32) + 64) * sizeof(uint32_t);
+  if (!configured) {
+    EIGKL_CUDA(cudaFuncSetAttribute(res_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(((size_t)2 * ((PLAN_MAX_N + 31) / 32) + 64) * sizeof(uint32_t))));
+    EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+    EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<8, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+    EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<16, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+    EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<24, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
+    configured = true;
+  }
+  res_plan_kernel<<<(unsigned)L.res_blocks, PLAN_THREADS, plan_smem, h->stream>>>(
+      L.rowptr.p, L.col.p, reinterpret_cast<const int4 *>(L.res_info.p), n, L.res_src.p, L.res_halo_ids.p, L.res_halo_cnt.p,
+      L.res_check.p);
+  EIGKL_CUDA(cudaGetLastError());
+  h->launches += 1;
+  EIGKL_CUDA(cudaMemcpyAsync(L.res_check_host, L.res_check.p, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+}
+
+void cheb_resident_plan_finish(eigkl_handle *h) {
+  auto &L = h->L;
+  if (L.res_blocks <= 0) return;
+  const int32_t max_span = L.res_check_host[0], max_rows = L.res_check_host[1], max_halo = L.res_check_host[2];
+  // 768 threads x 4 or 8 entries; the largest blocks run as 512 threads x 24 entries (128 registers per thread
+  // instead of 80: industry2 5.6 vs 6.8 ms per solve, ibm10 equal).  K = 16 (768 threads) is kept for tuning.
+  int k = 0;
+  if (max_span <= RES_THREADS * 4 - 1) k = 4;
+  else if (max_span <= RES_THREADS * 8 - 1) k = 8;
+  else if (max_span <= RES_CAP - 1) k = 24;
+  if (const char *ev = getenv("EIGKL_RES_K")) {                   // tuning aid
+    const int want = atoi(ev);
+    if ((want == 4 || want == 8 || want == 16 || want == 24) && want >= k && k != 0) k = want;
+  }
+  L.res_k = k;
+  if (getenv("EIGKL_RES_PHASES"))
+    fprintf(stderr, "resident plan: n %d nnz %lld blocks %d chunk %lld max span %d rows %d halo %d -> K %d\n", L.n, (long long)L.nnz,
+            L.res_blocks, (long long)L.res_chunk, max_span, max_rows, max_halo, k);
+  L.res_ok = k != 0 && max_rows > 0 && max_rows <= RES_MAXROWS && max_halo <= RES_MAXHALO;
+}
+
+bool cheb_resident_usable(const eigkl_handle *h) {
+  return h->spmv_resident && h->opts.nranks == 1 && h->L.valid && h->L.res_ok;
+}
+
+void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *scale, double *v_store, double *const w[3],
+                          const unsigned char *out_idx, int deg, double fc, double fe) {
+  auto &L = h->L;
+  EIGKL_REQUIRE(cheb_resident_usable(h) && deg >= 1 && deg <= 64, EIGKL_E_ARG, "resident filter not available");
+  ResidentArgs A{};
+  A.val = L.val.p; A.src = L.res_src.p;
+  A.info = reinterpret_cast<const int4 *>(L.res_info.p);
+  A.halo_ids = L.res_halo_ids.p; A.halo_cnt = L.res_halo_cnt.p;
+  A.x_in = x_in; A.scale = scale; A.v_store = v_store;
+  for (int b = 0; b < 3; ++b) A.w[b] = w[b];
+  A.ll = reinterpret_cast<uint4 *>(L.res_ll.p);
+  A.tag_base = L.res_tag;
+  A.n = L.n;
+  A.deg = deg; A.fc = fc; A.fe = fe;
+  static const bool phases = getenv("EIGKL_RES_PHASES") != nullptr;
+  A.phases = phases ? 1 : 0;
+  for (int k = 0; k < deg; ++k) A.out_idx[k] = out_idx[k];
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)L.res_blocks);
+  cfg.blockDim = dim3(L.res_k == 24 ? 512 : RES_THREADS);
+  cfg.dynamicSmemBytes = RES_SMEM;
+  cfg.stream = h->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeCooperative;       // every CTA resident at once: a CTA waits on its neighbours' values
+  attr[0].val.cooperative = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  if (L.res_k == 4) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<4, 768>, A));
+  else if (L.res_k == 8) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<8, 768>, A));
+  else if (L.res_k == 16) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<16, 768>, A));
+  else EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<24, 512>, A));
+  L.res_tag += (uint32_t)deg;
+  h->launches++;
 }
 
 // y = ca*s*(L x) + cb*s*x + cg*z for this rank's rows (s = *scale_inv or 1).
