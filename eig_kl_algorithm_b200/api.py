@@ -62,7 +62,8 @@ class Stats(C.Structure):
                 ("n_spmv", C.c_int64), ("n_multidot", C.c_int64), ("n_update", C.c_int64), ("n_restart", C.c_int64),
                 ("n_dvalues", C.c_int64),
                 ("bytes_spmv", C.c_double), ("bytes_dvalues", C.c_double),
-                ("bytes_multidot_total", C.c_double), ("bytes_update_total", C.c_double)]
+                ("bytes_multidot_total", C.c_double), ("bytes_update_total", C.c_double),
+                ("spmv_per_launch", C.c_int32), ("resident_k", C.c_int32)]
 
     def as_dict(self):
         d = {}

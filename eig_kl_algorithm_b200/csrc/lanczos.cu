@@ -503,6 +503,8 @@ void fiedler_solve(eigkl_handle *h) {
   // w = B x:  d SpMVs, recurrence fused.  x is either an un-normalised buffer (scale = 1/beta, v_j stored)
   // or an already normalised basis column (after a restart).  Returns the index of the buffer holding w.
   const bool resident = cheb_resident_usable(h) && deg >= 2 && deg <= 64;
+  h->stats.spmv_per_launch = resident ? deg : 1;
+  h->stats.resident_k = resident ? h->L.res_k : 0;
   auto apply_filter = [&](const double *x_in, const double *scale, double *v_store, const double *v_norm, int avoid) -> int {
     // profiling brackets the whole chain of `deg` back-to-back SpMVs with ONE event pair (single rank), so the
     // ~2 us an event pair costs is not charged to every 15 us launch

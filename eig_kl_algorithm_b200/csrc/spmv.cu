@@ -643,7 +643,8 @@ void cheb_resident_plan_finish(eigkl_handle *h) {
   else if (max_span <= RES_CAP - 1) k = 24;
   if (const char *ev = getenv("EIGKL_RES_K")) {                   // tuning aid
     const int want = atoi(ev);
-    if ((want == 4 || want == 8 || want == 16 || want == 24) && want >= k && k != 0) k = want;
+    const int cap = (want == 24 ? 512 : RES_THREADS) * want - 1;
+    if ((want == 4 || want == 8 || want == 16 || want == 24) && k != 0 && max_span <= cap) k = want;
   }
   L.res_k = k;
   if (getenv("EIGKL_RES_PHASES"))

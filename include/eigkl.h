@@ -85,6 +85,10 @@ typedef struct {
   /* algorithmic bytes of ONE launch of the kernel class at this problem size          */
   double   bytes_spmv, bytes_dvalues;
   double   bytes_multidot_total, bytes_update_total;   /* summed over the profiled launches        */
+  /* SpMVs carried by one launch of the SpMV kernel class: 1 (one spmv kernel per product), or the
+   * Chebyshev degree when the resident filter runs a whole filter application as one launch       */
+  int32_t  spmv_per_launch;
+  int32_t  resident_k;           /* entries per thread of the resident filter kernel, 0 = not used  */
 } eigkl_stats;
 
 /* KL trace, one row per swap plus row 0 (the initial cut) -- the rows cKL writes to

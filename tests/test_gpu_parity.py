@@ -308,6 +308,38 @@ def test_plain_lanczos_flag_matches_filtered(handles, oracle, workdir):
     assert out["filtered"][2]["lanczos_steps"] * 4 < out["plain"][2]["lanczos_steps"]     # the point of the filter
 
 
+@pytest.mark.parametrize("c,env_k", [("fract", None), ("ibm01", None), ("ibm01", "16"), ("ibm01", "24"), ("industry2", None),
+                                     ("industry2", "16"), ("ibm10", None)])
+def test_resident_filter_matches_per_spmv_launches(c, env_k, workdir, monkeypatch):
+    """The resident polynomial filter (a whole Chebyshev filter application as one cooperative launch: matrix in
+    registers, x in shared memory, halo exchanged through L2) against the path with one kernel launch per SpMV,
+    in every entries-per-thread variant of the kernel."""
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EIGKL_SPMV_RESIDENT", mode)
+        if env_k:
+            monkeypatch.setenv("EIGKL_RES_K", env_k)
+        with api.Handle() as h:
+            h.load_hgr(os.path.join(workdir, "circuit", c + ".hgr"))
+            h.assemble_laplacian()
+            lam, v = h.fiedler()
+            lam2, v2 = h.fiedler()
+            assert lam == lam2 and np.array_equal(v, v2)                  # no order dependence in the halo exchange
+            r = np.linalg.norm(h.spmv(v) - lam * v)
+            res[mode] = (lam, v, h.stats(), r)
+    s0, s1 = res["0"][2], res["1"][2]
+    assert s0["resident_k"] == 0 and s0["spmv_per_launch"] == 1
+    assert s1["spmv_per_launch"] == 16 and s1["resident_k"] == (int(env_k) if env_k else s1["resident_k"])
+    assert s1["resident_k"] in (4, 8, 16, 24)
+    assert s0["converged"] == 1 and s1["converged"] == 1
+    assert s1["matvecs"] == s0["matvecs"]                                 # same iteration, different plumbing
+    assert s1["gpu_launches"] < s0["gpu_launches"]
+    assert abs(res["0"][0] - res["1"][0]) <= 1e-10 * res["0"][0]
+    cs = abs(res["0"][1] @ res["1"][1])
+    assert np.sqrt(max(0.0, 1.0 - cs * cs)) <= 1e-6
+    assert res["0"][3] < 1e-9 and res["1"][3] < 1e-9
+
+
 @pytest.mark.parametrize("n", [8, 12, 31])
 def test_tiny_graphs(n, oracle, tmp_path):
     """Smallest sizes the reference's ncv = min(100, n/2) rule allows: a ring of 2-pin nets plus one chord net."""

@@ -91,6 +91,7 @@ def test_ibm18_sized_synthetic_eig_properties(synth1):
         assert abs(lam) < 1e-10                                    # disconnected: second eigenvalue is 0 too
         assert np.linalg.norm(h.spmv(v) - lam * v) < 1e-9          # a genuine eigenpair
         assert st["resid_est"][1] < 1e-9
+        assert st["resident_k"] == 0 and st["spmv_per_launch"] == 1   # too large to stay on chip: one launch per SpMV
         med, side = h.partition_from_fiedler()
         assert np.array_equal(side, (med > v).astype(np.uint8))    # cEIG.cpp:218
         s = np.sort(v)
