@@ -225,6 +225,8 @@ struct EigState {
   DBuf<double> scal;           // [0] norm^2, [1] 1/beta, ...
   DBuf<unsigned int> counters; // last-block-done counters
   DBuf<int> flag;              // [0] = 1: second Gram-Schmidt pass of the current step is skipped
+  DBuf<double> gs_partial;     // fused Gram-Schmidt kernel: per-CTA partial dot products / norms
+  DBuf<unsigned int> gs_sync;  // [0] grid-barrier arrivals (monotonic within a solve), [1] last-CTA ticket
   DBuf<double> Y;              // ncv*ncv restart coefficients (column major, ld = ncv)
   DBuf<double> xfull;          // nranks * n_pad : all-gathered SpMV input (multi-rank only)
   DBuf<double> fiedler;        // n : result vector, file node ids
@@ -259,6 +261,8 @@ struct eigkl_handle {
   int spmv_mode = 0;           // EIGKL_SPMV_MODE: 0 auto (flat), 1 staged, 2 sub-warp, 3 flat (tuning aid)
   int spmv_pdl = 1;            // EIGKL_SPMV_PDL=0 disables programmatic dependent launch of the SpMV chain
   int spmv_resident = 1;       // EIGKL_SPMV_RESIDENT=0: one launch per SpMV even when the matrix fits on chip
+  int gs_fused = 1;            // EIGKL_GS_FUSED=0: Gram-Schmidt as separate multidot / update launches
+  int coop_launch = 1;         // EIGKL_COOP=0: launch the grid-synchronising kernels without the cooperative attribute (tuning aid)
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
   // scratch of the sort / scan primitives

@@ -226,6 +226,245 @@ update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__rest
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Fused Gram-Schmidt: both passes of a Lanczos step (h1 = V^T w, w -= V h1, h2 = V^T w, w -= V h2, the
+// DGKS decision, alpha_j, beta_j, 1/beta_j) as ONE cooperative launch instead of four.
+//
+// The separate kernels stream the basis four times per step and, on the circuits, spend most of their
+// ~14 us each on launch/drain and the last-block folds.  Here one CTA per SM owns a fixed slice of R rows;
+// its slice of w and as many basis columns as fit (cache_cols of them, all of them up to ~20 K rows) stay in
+// shared memory across the passes, so the basis is read from L2/HBM ONCE per step.  The three global
+// reductions are per-CTA partials + a grid barrier, after which EVERY CTA folds the partials in the same
+// fixed order (so all CTAs take the same DGKS decision and the result is bit-reproducible).  The second
+// dot products are computed before the decision is known (they only read shared memory), which saves a
+// barrier; the final norm is folded by the last CTA to finish (ticket), not behind a barrier.
+// Single rank only (the multi-rank path needs NCCL all-reduces between the passes), rows/CTA <= 2048.
+// ---------------------------------------------------------------------------------------------------
+constexpr int GS_THREADS = 1024;
+constexpr int GS_MAX_ROWS = 2048;
+struct GsArgs {
+  const double *V;
+  size_t ld;
+  int ncols;
+  double *w;
+  int32_t n;
+  int R;                 // rows per CTA, a multiple of 32
+  int cache_cols;        // basis columns kept in shared memory
+  int hs_cap;            // capacity of the coefficient array in shared memory (>= ncols + 1)
+  double *p1, *p2, *p3;  // partials: [ncols][G], [ncols + 1][G] (last row: |w|^2 after pass 1), [G]
+  unsigned int *barrier, *ticket;
+  unsigned int base;
+  double *scal, *beta_out, *alpha_out;
+  int j;
+  double eta2;
+  int *flag;
+};
+
+__device__ __forceinline__ void gs_grid_barrier(unsigned int *ctr, unsigned int target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory");
+    } while ((int)(v - target) < 0);
+  }
+  __syncthreads();
+}
+
+// sum over the block, same value in every thread, fixed order
+__device__ __forceinline__ double gs_block_sum(double v, double *red) {
+  v = warp_sum(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < GS_THREADS / 32; ++i) s += red[i];
+  __syncthreads();
+  return s;
+}
+
+// P[c * G + cta] = sum_r V[c][row0 + r] * ws[r]; FILL: first touch of the basis, columns < cache_cols are kept.
+// One warp per column.  Columns read from global memory keep 8 independent loads per lane in flight (the
+// first version had 4 and one dependent round trip per 128 rows: 30 us per step on ibm10 instead of ~10).
+template <bool FILL>
+__device__ __forceinline__ void gs_dots(const GsArgs &A, const double *ws, double *Vs, int32_t row0, int32_t rows, double *P) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int R = A.R;
+  const int ncached = FILL ? 0 : min(A.cache_cols, A.ncols);
+  for (int c = warp; c < ncached; c += GS_THREADS / 32) {           // from shared memory
+    const double *vs = Vs + (size_t)c * R;
+    double acc0 = 0.0, acc1 = 0.0;
+    int r = lane;
+    for (; r + 32 < R; r += 64) { acc0 += vs[r] * ws[r]; acc1 += vs[r + 32] * ws[r + 32]; }
+    if (r < R) acc0 += vs[r] * ws[r];
+    const double s = warp_sum(acc0 + acc1);
+    if (lane == 0) P[(size_t)c * gridDim.x + blockIdx.x] = s;
+  }
+  for (int c = ncached + warp; c < A.ncols; c += GS_THREADS / 32) {  // from L2 / HBM
+    const double *col = A.V + (size_t)c * A.ld + row0;
+    double *vs = Vs + (size_t)c * R;
+    const bool keep = FILL && c < A.cache_cols;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int r = lane; r < R; r += 256) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = (r + 32 * u < rows) ? col[r + 32 * u] : 0.0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int rr = r + 32 * u;
+        if (rr < R) {
+          if (keep) vs[rr] = v[u];
+          if (u & 1) acc1 += v[u] * ws[rr]; else acc0 += v[u] * ws[rr];
+        }
+      }
+    }
+    const double s = warp_sum(acc0 + acc1);
+    if (lane == 0) P[(size_t)c * gridDim.x + blockIdx.x] = s;
+  }
+}
+
+// hs[c] = sum over the CTAs of P[c][.], identical in every CTA (fixed order)
+__device__ __forceinline__ void gs_fold(const double *P, int cnt, double *hs) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned G = gridDim.x;
+  for (int c = warp; c < cnt; c += GS_THREADS / 32) {
+    const double *pc = P + (size_t)c * G;
+    double v[5];
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {                                  // 160 CTAs' worth of loads in flight at once
+      const unsigned b = lane + 32u * k;
+      v[k] = b < G ? __ldcg(pc + b) : 0.0;
+    }
+    double s = ((v[0] + v[1]) + (v[2] + v[3])) + v[4];
+    for (unsigned b = lane + 160u; b < G; b += 32) s += __ldcg(pc + b);
+    s = warp_sum(s);
+    if (lane == 0) hs[c] = s;
+  }
+}
+
+// ws[r] -= sum_c V[c][r] * hs[c]; returns this thread's share of |w|^2 afterwards
+__device__ __forceinline__ double gs_update(const GsArgs &A, double *ws, const double *Vs, const double *hs, double *comb,
+                                            int32_t row0, int32_t rows) {
+  const int tid = threadIdx.x;
+  const int R = A.R;
+  const int S = R >= GS_THREADS ? 1 : GS_THREADS / R;              // column splits per row (warp-uniform: R % 32 == 0)
+  double nrm = 0.0;
+  for (int base = 0; base < R; base += GS_THREADS) {
+    const int r = S == 1 ? base + tid : tid % R;
+    const int q = S == 1 ? 0 : tid / R;
+    const bool active = S == 1 ? r < R : q < S;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (active) {
+      const int ncached = min(A.cache_cols, A.ncols);
+      int c = q;
+      for (; c + S < ncached; c += 2 * S) {                        // from shared memory
+        acc0 += Vs[(size_t)c * R + r] * hs[c];
+        acc1 += Vs[(size_t)(c + S) * R + r] * hs[c + S];
+      }
+      for (; c < ncached; c += S) acc0 += Vs[(size_t)c * R + r] * hs[c];
+      // c is now this thread's first column beyond the cache: 8 independent loads in flight
+      const double *vp = A.V + row0 + r;
+      const bool in = r < rows;
+      for (; c < A.ncols; c += 8 * S) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = (in && c + u * S < A.ncols) ? vp[(size_t)(c + u * S) * A.ld] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          if (c + u * S < A.ncols) {
+            if (u & 1) acc1 += v[u] * hs[c + u * S]; else acc0 += v[u] * hs[c + u * S];
+          }
+      }
+    }
+    double tot = acc0 + acc1;
+    if (S > 1) {
+      if (active) comb[q * R + r] = tot;
+      __syncthreads();
+      if (active && q == 0) {
+        tot = 0.0;
+        for (int qq = 0; qq < S; ++qq) tot += comb[qq * R + r];
+      }
+      __syncthreads();
+    }
+    if (active && q == 0) {
+      const double wn = ws[r] - tot;
+      ws[r] = wn;
+      nrm += wn * wn;
+    }
+  }
+  return nrm;
+}
+
+__global__ void __launch_bounds__(GS_THREADS, 1) gs_fused_kernel(const GsArgs A) {
+  extern __shared__ __align__(16) double gsm[];
+  double *ws = gsm;                         // R: this CTA's slice of w
+  double *hs = ws + A.R;                    // hs_cap: h1, then h2 (+ the folded |w|^2)
+  double *red = hs + A.hs_cap;              // 32
+  double *comb = red + 32;                  // GS_THREADS: column-split partial sums of the update
+  double *Vs = comb + GS_THREADS;           // cache_cols * R
+  __shared__ bool am_last;
+  const int tid = threadIdx.x;
+  const unsigned G = gridDim.x;
+  const int32_t row0 = (int32_t)blockIdx.x * A.R;
+  const int32_t rows = max(0, min(A.R, A.n - row0));
+  for (int r = tid; r < A.R; r += GS_THREADS) ws[r] = r < rows ? A.w[row0 + r] : 0.0;
+  __syncthreads();
+  gs_dots<true>(A, ws, Vs, row0, rows, A.p1);
+  gs_grid_barrier(A.barrier, A.base + G);
+  gs_fold(A.p1, A.ncols, hs);
+  __syncthreads();
+  double hq[4] = {0.0, 0.0, 0.0, 0.0};
+  for (int c = 0; c < A.ncols; ++c) hq[c & 3] += hs[c] * hs[c];
+  const double hh = (hq[0] + hq[1]) + (hq[2] + hq[3]);
+  const double h1j = hs[A.j];
+  const double n1 = gs_block_sum(gs_update(A, ws, Vs, hs, comb, row0, rows), red);
+  gs_dots<false>(A, ws, Vs, row0, rows, A.p2);
+  if (tid == 0) A.p2[(size_t)A.ncols * G + blockIdx.x] = n1;
+  gs_grid_barrier(A.barrier, A.base + 2 * G);
+  gs_fold(A.p2, A.ncols + 1, hs);
+  __syncthreads();
+  const double s1 = hs[A.ncols];
+  // DGKS: |w_after|^2 > eta^2 (|w_after|^2 + |h|^2)  <=>  the first pass lost at most eps/eta of orthogonality
+  if (s1 > A.eta2 * (s1 + hh)) {
+    for (int r = tid; r < rows; r += GS_THREADS) A.w[row0 + r] = ws[r];
+    if (blockIdx.x == 0 && tid == 0) {
+      const double beta = sqrt(s1);
+      A.scal[0] = s1;
+      A.scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
+      A.beta_out[A.j] = beta;
+      A.alpha_out[A.j] = h1j;
+      *A.flag = 1;
+    }
+    return;
+  }
+  const double h2j = hs[A.j];
+  const double n2 = gs_block_sum(gs_update(A, ws, Vs, hs, comb, row0, rows), red);
+  for (int r = tid; r < rows; r += GS_THREADS) A.w[row0 + r] = ws[r];
+  if (tid == 0) {
+    A.p3[blockIdx.x] = n2;
+    __threadfence();
+    am_last = (atomicInc(A.ticket, G - 1) == G - 1);
+  }
+  __syncthreads();
+  if (!am_last) return;
+  __threadfence();
+  double s = 0.0;
+  if (tid < 32) {
+    for (unsigned b = tid; b < G; b += 32) s += __ldcg(&A.p3[b]);
+    s = warp_sum(s);
+    if (tid == 0) {
+      const double beta = sqrt(s);
+      A.scal[0] = s;
+      A.scal[1] = beta > 0.0 ? 1.0 / beta : 0.0;
+      A.beta_out[A.j] = beta;
+      A.alpha_out[A.j] = h1j + h2j;
+      *A.flag = 0;
+    }
+  }
+}
+
 // multi-rank, after the all-reduce of |w|^2 (scal[0]): the pass-1 decision ...
 __global__ void decide_kernel(double *__restrict__ scal, const double *__restrict__ h1, int ncols, double eta2,
                               int *__restrict__ flag, double *__restrict__ beta_out, double *__restrict__ alpha_out, int j) {
@@ -331,6 +570,11 @@ struct LzCtx {
   size_t ld;        // leading dimension of the local basis slice (= n_pad)
   int gx_md, gx_up;
   double eta2;      // DGKS threshold squared
+  // fused Gram-Schmidt kernel (single rank, small enough row slices): grid, rows per CTA, cached columns
+  bool gs_fused = false;
+  int gs_grid = 0, gs_rows = 0, gs_cache = 0, gs_hs_cap = 0;
+  size_t gs_smem = 0;
+  unsigned int gs_base = 0;
 };
 
 void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out, int pass) {
@@ -403,6 +647,30 @@ void launch_norm(LzCtx &c, const double *w) {
 // full Gram-Schmidt (twice) of w against V[:, 0..j]; leaves alpha_j, beta_j, 1/beta_j on the device
 void orthogonalise(LzCtx &c, double *V, int j, double *w) {
   auto &e = c.h->eig;
+  if (c.gs_fused) {
+    GsArgs A{};
+    A.V = V; A.ld = c.ld; A.ncols = j + 1; A.w = w; A.n = c.nl;
+    A.R = c.gs_rows; A.cache_cols = c.gs_cache; A.hs_cap = c.gs_hs_cap;
+    const size_t G = (size_t)c.gs_grid;
+    A.p1 = e.gs_partial.p; A.p2 = A.p1 + (size_t)(c.m + 2) * G; A.p3 = A.p2 + (size_t)(c.m + 3) * G;
+    A.barrier = e.gs_sync.p; A.ticket = e.gs_sync.p + 1; A.base = c.gs_base;
+    A.scal = e.scal.p; A.beta_out = e.beta.p; A.alpha_out = e.alpha.p; A.j = j; A.eta2 = c.eta2; A.flag = e.flag.p;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)c.gs_grid); cfg.blockDim = dim3(GS_THREADS); cfg.stream = c.h->stream;
+    cfg.dynamicSmemBytes = c.gs_smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeCooperative;     // the CTAs wait for each other at the two grid barriers
+    attr[0].val.cooperative = c.h->coop_launch ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    c.h->prof.begin(KC_MULTIDOT, c.h->stream);
+    EIGKL_CUDA(cudaLaunchKernelEx(&cfg, gs_fused_kernel, A));
+    c.h->prof.end(c.h->stream);
+    c.gs_base += 2u * (unsigned int)c.gs_grid;
+    c.h->launches++;
+    // algorithmic bytes: the basis once, w in and out
+    c.h->stats.bytes_multidot_total += c.h->prof.on ? ((double)(j + 1) * c.nl * 8.0 + (double)c.nl * 16.0) : 0.0;
+    return;
+  }
   double *h1 = e.hcoef.p, *h2 = e.hcoef.p + (c.m + 1);
   launch_multidot(c, V, j + 1, w, h1, 1);
   launch_update(c, V, j + 1, w, h1, nullptr, j, 1);      // sets flag = 1 when the second pass can be skipped
@@ -502,6 +770,34 @@ void fiedler_solve(eigkl_handle *h) {
 
   // w = B x:  d SpMVs, recurrence fused.  x is either an un-normalised buffer (scale = 1/beta, v_j stored)
   // or an already normalised basis column (after a restart).  Returns the index of the buffer holding w.
+  // ---- fused Gram-Schmidt kernel: one CTA per SM, its rows of w and of the first gs_cache basis columns in shared memory ----
+  c.gs_fused = false;
+  if (c.R == 1 && h->gs_fused && n >= 64) {
+    const int G = (int)std::min<int64_t>(h->sm_count, ceil_div(n, 64));
+    const int Rr = (int)(ceil_div(ceil_div(n, G), 32) * 32);
+    if (Rr <= GS_MAX_ROWS) {
+      const size_t budget = 227 * 1024 - 2048;
+      const int hs_cap = m + 4;
+      const size_t fixed = ((size_t)Rr + hs_cap + 32 + GS_THREADS) * sizeof(double);
+      int cache = (int)std::min<size_t>((size_t)m + 1, (budget - fixed) / ((size_t)Rr * sizeof(double)));
+      if (const char *ev = getenv("EIGKL_GS_CACHE")) cache = std::max(0, std::min(cache, atoi(ev)));   // tuning aid
+      c.gs_fused = true;
+      c.gs_grid = (int)ceil_div(n, Rr);
+      c.gs_rows = Rr; c.gs_cache = cache; c.gs_hs_cap = hs_cap;
+      c.gs_smem = fixed + (size_t)cache * Rr * sizeof(double);
+      c.gs_base = 0;
+      e.gs_partial.ensure((size_t)(2 * m + 8) * c.gs_grid);
+      e.gs_sync.ensure(2);
+      EIGKL_CUDA(cudaMemsetAsync(e.gs_sync.p, 0, 2 * sizeof(unsigned int), st));
+      static bool gs_configured = false;
+      if (!gs_configured) {
+        EIGKL_CUDA(cudaFuncSetAttribute(gs_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
+        gs_configured = true;
+      }
+    }
+  }
+  h->stats.gs_fused = c.gs_fused ? 1 : 0;
+  h->stats.gs_cache_cols = c.gs_fused ? c.gs_cache : 0;
   const bool resident = cheb_resident_usable(h) && deg >= 2 && deg <= 64;
   h->stats.spmv_per_launch = resident ? deg : 1;
   h->stats.resident_k = resident ? h->L.res_k : 0;

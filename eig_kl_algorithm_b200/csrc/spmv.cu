@@ -681,7 +681,7 @@ void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *sca
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;       // every CTA resident at once: a CTA waits on its neighbours' values
-  attr[0].val.cooperative = 1;
+  attr[0].val.cooperative = h->coop_launch ? 1 : 0;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (L.res_k == 4) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<4, 768>, A));
   else if (L.res_k == 8) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<8, 768>, A));

@@ -89,6 +89,10 @@ typedef struct {
    * Chebyshev degree when the resident filter runs a whole filter application as one launch       */
   int32_t  spmv_per_launch;
   int32_t  resident_k;           /* entries per thread of the resident filter kernel, 0 = not used  */
+  /* 1 when both Gram-Schmidt passes of a Lanczos step run as ONE cooperative launch (counted in
+   * n_multidot / ms_multidot; n_update stays 0), 0 when they are separate multidot/update launches */
+  int32_t  gs_fused;
+  int32_t  gs_cache_cols;        /* basis columns the fused kernel keeps in shared memory            */
 } eigkl_stats;
 
 /* KL trace, one row per swap plus row 0 (the initial cut) -- the rows cKL writes to

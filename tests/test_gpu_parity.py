@@ -340,6 +340,35 @@ def test_resident_filter_matches_per_spmv_launches(c, env_k, workdir, monkeypatc
     assert res["0"][3] < 1e-9 and res["1"][3] < 1e-9
 
 
+@pytest.mark.parametrize("c,cache", [("fract", None), ("ibm01", None), ("ibm01", "7"), ("ibm01", "0"), ("ibm10", None)])
+def test_fused_gram_schmidt_matches_separate_kernels(c, cache, workdir, monkeypatch):
+    """Both Gram-Schmidt passes of a Lanczos step as one cooperative launch (basis slice cached in shared memory,
+    grid barriers between the reductions) against the separate multidot / update launches; `cache` limits the
+    number of basis columns kept on chip so that the re-read-from-L2 path runs too."""
+    res = {}
+    for mode in ("0", "1"):
+        monkeypatch.setenv("EIGKL_GS_FUSED", mode)
+        if cache is not None:
+            monkeypatch.setenv("EIGKL_GS_CACHE", cache)
+        with api.Handle() as h:
+            h.load_hgr(os.path.join(workdir, "circuit", c + ".hgr"))
+            h.assemble_laplacian()
+            lam, v = h.fiedler()
+            lam2, v2 = h.fiedler()
+            assert lam == lam2 and np.array_equal(v, v2)                  # fixed-order folds: bit-reproducible
+            res[mode] = (lam, v, h.stats(), np.linalg.norm(h.spmv(v) - lam * v))
+    s0, s1 = res["0"][2], res["1"][2]
+    assert s0["gs_fused"] == 0 and s1["gs_fused"] == 1
+    if cache is not None:
+        assert s1["gs_cache_cols"] == int(cache)
+    assert s0["converged"] == 1 and s1["converged"] == 1
+    assert s1["lanczos_steps"] == s0["lanczos_steps"] and s1["gpu_launches"] < s0["gpu_launches"]
+    assert abs(res["0"][0] - res["1"][0]) <= 1e-10 * res["0"][0]
+    cs = abs(res["0"][1] @ res["1"][1])
+    assert np.sqrt(max(0.0, 1.0 - cs * cs)) <= 1e-6
+    assert res["0"][3] < 1e-9 and res["1"][3] < 1e-9
+
+
 @pytest.mark.parametrize("n", [8, 12, 31])
 def test_tiny_graphs(n, oracle, tmp_path):
     """Smallest sizes the reference's ncv = min(100, n/2) rule allows: a ring of 2-pin nets plus one chord net."""
