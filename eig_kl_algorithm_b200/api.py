@@ -64,7 +64,8 @@ class Stats(C.Structure):
                 ("bytes_spmv", C.c_double), ("bytes_dvalues", C.c_double),
                 ("bytes_multidot_total", C.c_double), ("bytes_update_total", C.c_double),
                 ("spmv_per_launch", C.c_int32), ("resident_k", C.c_int32),
-                ("gs_fused", C.c_int32), ("gs_cache_cols", C.c_int32)]
+                ("gs_fused", C.c_int32), ("gs_cache_cols", C.c_int32),
+                ("kl_local", C.c_int32), ("reserved0", C.c_int32)]
 
     def as_dict(self):
         d = {}

@@ -570,6 +570,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   h->launches++;
   EIGKL_CUDA(cudaGetLastError());
   A.valid = true;
+  A.nb_valid = false;
   h->stats.nnz_kl = A.nnz;
   // algorithmic bytes of one full D-value pass: nnz*(4 w + 4 col) + n*(4 rowptr + 1 side + 4 out)  
   h->stats.bytes_dvalues = (double)A.nnz * 8.0 + (double)n * 9.0;

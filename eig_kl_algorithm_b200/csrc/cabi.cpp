@@ -133,6 +133,7 @@ int eigkl_create(eigkl_handle **out, const eigkl_opts *opts) {
     if (const char *m = getenv("EIGKL_SPMV_RESIDENT")) h->spmv_resident = atoi(m);
     if (const char *m = getenv("EIGKL_GS_FUSED")) h->gs_fused = atoi(m);
     if (const char *m = getenv("EIGKL_COOP")) h->coop_launch = atoi(m);
+    if (const char *m = getenv("EIGKL_KL_LOCAL")) h->kl_local = atoi(m);
     h->stats.struct_size = sizeof(eigkl_stats);
     if (h->opts.nranks > 1) comm_init(h);
     *out = h;

@@ -12,13 +12,14 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_MASK, v, o);
   return v;
 }
+// max of a 64-bit key over the warp, all lanes get it: two redux.sync (hardware warp reductions) -- the high
+// words first, then the low words of the lanes that hold the winning high word -- instead of a five-round
+// butterfly of 64-bit shuffles (10 SHFL + 20 ALU on the KL swap loop's critical path)
 __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    unsigned long long t = __shfl_xor_sync(FULL_MASK, v, o);
-    v = t > v ? t : v;
-  }
-  return v;
+  const unsigned hi = (unsigned)(v >> 32), lo = (unsigned)v;
+  const unsigned mhi = __reduce_max_sync(FULL_MASK, hi);
+  const unsigned mlo = __reduce_max_sync(FULL_MASK, hi == mhi ? lo : 0u);
+  return ((unsigned long long)mhi << 32) | mlo;
 }
 
 // monotone float -> uint32 map (a < b  <=>  ord(a) < ord(b)); -0.0f is folded onto +0.0f first so

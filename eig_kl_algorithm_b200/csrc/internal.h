@@ -191,6 +191,8 @@ struct KlCsr {                 // fp32, symmetric, rows in reference traversal o
   DBuf<float> w;
   int32_t n_blocks = 0;        // row blocks of the staged D-value kernel
   DBuf<int32_t> blk_row;
+  DBuf<int32_t> nb;            // 2 per entry: rowptr[col], rowptr[col + 1] (the shared-memory swap loop's one-load lookup)
+  bool nb_valid = false;
   bool valid = false;
 };
 
@@ -262,6 +264,7 @@ struct eigkl_handle {
   int spmv_pdl = 1;            // EIGKL_SPMV_PDL=0 disables programmatic dependent launch of the SpMV chain
   int spmv_resident = 1;       // EIGKL_SPMV_RESIDENT=0: one launch per SpMV even when the matrix fits on chip
   int gs_fused = 1;            // EIGKL_GS_FUSED=0: Gram-Schmidt as separate multidot / update launches
+  int kl_local = 1;            // EIGKL_KL_LOCAL=0: never run the swap loop with its state in shared memory
   int coop_launch = 1;         // EIGKL_COOP=0: launch the grid-synchronising kernels without the cooperative attribute (tuning aid)
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel

@@ -626,6 +626,304 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
 #undef KL_PHASE
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// The swap loop with its working state in shared memory (single rank, n <= KL_LOCAL_MAX_N).
+//
+// kl_loop_kernel above is a chain of ~10 dependent L2 round trips per swap (tile keys -> order[] -> row
+// pointers -> neighbour id -> its row pointers -> its entries -> their side bytes -> D store | stamp
+// atomics -> tile rescan loads -> key stores) at ~1 us each from one SM: 8.8 us per swap on ibm10
+// whatever the bandwidth.  One CTA can hold what the chain keeps re-fetching:
+//   * the tile keys and the rescan stamps / work list (20 bytes per 256 nodes),
+//   * the side / locked bits of EVERY node, 2 bits each (ibm10: 17 KB; 128 KB at the 524 288-node limit),
+// an auxiliary array gives, for every CSR entry, the row extent of the neighbour it names (one load yields
+// v, rowptr[v], rowptr[v+1]), a warp issues the loads of ALL its neighbour rows before it sums the first,
+// and a recomputed D-value updates its tile's key with one shared-memory atomicMax -- a tile is rescanned
+// only when the node that held its best key was itself touched or locked (2-4 tiles per swap, spread over
+// the warps, instead of every touched tile).  Per swap: row pointers of (a, b) -> neighbour entries -> the
+// neighbours' rows | D-values of the few tiles to rescan: four round trips.
+// When the remain[] orders are ascending node ids (the -EIG start, cKL.cpp:155-174) the tie-break field of a
+// key is the node id itself, so the selected key names the node without the order[] / rank[] loads.
+// The arithmetic (order of the fp32 additions, first-max selection, gain, termination) is unchanged:
+// traces stay byte-identical to cKL.cpp's.
+// ---------------------------------------------------------------------------------------------------
+constexpr int32_t KL_LOCAL_MAX_N = 524288;
+
+__device__ __forceinline__ unsigned bits_get(const uint32_t *bits, int32_t u) { return (bits[u >> 4] >> ((u & 15) * 2)) & 3u; }
+
+// as warp_row_value, sides from the shared-memory bits; (c, ww) = this lane's entry of the row's first 32, already loaded
+__device__ __forceinline__ float warp_row_value_local(const int32_t *__restrict__ col, const float *__restrict__ w,
+                                                      const uint32_t *bits, int32_t lo, int32_t hi, int32_t ov_a, int32_t ov_b,
+                                                      int lane, int32_t c, float ww) {
+  float E = 0.0f, I = 0.0f;
+  for (int32_t base = lo; base < hi; base += 32) {
+    const bool valid = (base + lane) < hi;
+    int32_t cn = 0;
+    float wn = 0.0f;
+    const int32_t in = base + 32 + lane;
+    if (in < hi) { cn = __ldg(col + in); wn = __ldg(w + in); }   // next 32 entries while this chunk is summed
+    float x = 0.0f;
+    if (valid) {
+      unsigned sd;
+      if (c == ov_a) sd = 1u;
+      else if (c == ov_b) sd = 0u;
+      else sd = bits_get(bits, c) & ST_SIDE;
+      x = sd ? ww : -ww;
+    }
+    const int cnt = min(32, hi - base);
+    for (int t = 0; t < cnt; ++t) {
+      const float xt = __shfl_sync(FULL_MASK, x, t);
+      E = __fadd_rn(E, fmaxf(xt, 0.0f));
+      I = __fadd_rn(I, fmaxf(-xt, 0.0f));
+    }
+    c = cn; ww = wn;
+  }
+  return __fsub_rn(E, I);
+}
+
+template <bool ASC>
+__device__ __forceinline__ unsigned long long kl_key(float v, unsigned side, uint32_t ident) {
+  return ((unsigned long long)float_orderable(side ? -v : v) << 32) | (unsigned long long)(0xFFFFFFFFu - ident);
+}
+
+// best keys of one tile (both sides); one L2 round trip (the D-values, and the ranks unless ASC)
+template <bool ASC>
+__device__ __forceinline__ void tile_scan_local(const uint32_t *bits, const float *val, const uint32_t *__restrict__ rank, int32_t n,
+                                                int32_t tile, int lane, unsigned long long *keys) {
+  unsigned long long k0 = 0ull, k1 = 0ull;
+  const int32_t base = tile * KL_TILE;
+  float vv[KL_TILE / 32];
+  uint32_t id[KL_TILE / 32];
+#pragma unroll
+  for (int r = 0; r < KL_TILE / 32; ++r) {
+    const int32_t u = base + r * 32 + lane;
+    vv[r] = u < n ? __ldcg(val + u) : 0.0f;
+    id[r] = ASC ? (uint32_t)u : (u < n ? __ldg(rank + u) : 0u);
+  }
+#pragma unroll
+  for (int r = 0; r < KL_TILE / 32; ++r) {
+    const int32_t u = base + r * 32 + lane;
+    const unsigned st = u < n ? bits_get(bits, u) : ST_LOCK;
+    if (!(st & ST_LOCK)) {
+      const unsigned long long key = kl_key<ASC>(vv[r], st & ST_SIDE, id[r]);
+      if (st & ST_SIDE) k1 = key > k1 ? key : k1;
+      else k0 = key > k0 ? key : k0;
+    }
+  }
+  k0 = warp_max_u64(k0);
+  k1 = warp_max_u64(k1);
+  if (lane == 0) { keys[2 * tile] = k0; keys[2 * tile + 1] = k1; }
+}
+
+struct KlLocalParams {
+  int32_t n, n_tiles;
+  const int32_t *rowptr, *col;
+  const int2 *nb;                   // per entry: row extent of the neighbour it names
+  const float *w;
+  uint8_t *state;
+  const uint32_t *rank;
+  const int32_t *order0, *order1;
+  float *val;
+  float *t_cut, *t_gain;
+  int32_t *t_n1, *t_n2;
+  int64_t *ctrl;
+  float cut0;
+  uint32_t term_limit;
+  int64_t n0, n1;
+};
+
+__global__ void nb_extent_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t nnz, int2 *__restrict__ nb) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nnz) {
+    const int32_t v = col[i];
+    nb[i] = make_int2(rowptr[v], rowptr[v + 1]);
+  }
+}
+
+template <bool ASC>
+__global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const KlLocalParams p) {
+  extern __shared__ __align__(16) unsigned char kl_sm[];
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(kl_sm);      // 2 * n_tiles
+  uint32_t *stamps = reinterpret_cast<uint32_t *>(keys + 2 * (size_t)p.n_tiles);  // n_tiles
+  int32_t *list = reinterpret_cast<int32_t *>(stamps + p.n_tiles);                // n_tiles: tiles to rescan this swap
+  uint32_t *bits = reinterpret_cast<uint32_t *>(list + p.n_tiles);                // ceil(n / 16)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  __shared__ unsigned long long red0[32], red1[32];
+  __shared__ unsigned long long sh_best[2];
+  __shared__ float sh_cut;
+  __shared__ uint32_t sh_term, sh_iter;
+  __shared__ int sh_done, sh_nlist;
+  __shared__ long long sh_rem0, sh_rem1;
+  if (tid == 0) {
+    sh_cut = p.cut0; sh_term = 0; sh_iter = 0; sh_rem0 = p.n0; sh_rem1 = p.n1; sh_nlist = 0;
+    sh_done = (p.n0 <= 0 || p.n1 <= 0) ? 1 : 0;
+  }
+  // side / locked bits of every node: 16 nodes per word
+  const int32_t n_words = (p.n + 15) >> 4;
+  for (int32_t wd = tid; wd < n_words; wd += KL_LOOP_THREADS) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int32_t u = wd * 16 + q;
+      const unsigned st = u < p.n ? (unsigned)p.state[u] & 3u : ST_LOCK;
+      v |= st << (2 * q);
+    }
+    bits[wd] = v;
+  }
+  for (int32_t t = tid; t < p.n_tiles; t += KL_LOOP_THREADS) stamps[t] = 0u;
+  __syncthreads();
+  for (int32_t t = warp; t < p.n_tiles; t += KL_LOOP_THREADS / 32) tile_scan_local<ASC>(bits, p.val, p.rank, p.n, t, lane, keys);
+  __syncthreads();
+  uint32_t it_local = 0;
+#ifdef EIGKL_KL_CLOCKS
+  long long tph[6] = {0, 0, 0, 0, 0, 0};
+  long long tprev = clock64();
+#define KL_PHASE(i) do { if (tid == 0) { const long long t_ = clock64(); tph[i] += t_ - tprev; tprev = t_; } } while (0)
+#else
+#define KL_PHASE(i) do { } while (0)
+#endif
+
+  while (!sh_done) {
+    // ---- S1: best pair over the tile keys (shared memory) ----
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    for (int32_t t = tid; t < p.n_tiles; t += KL_LOOP_THREADS) {
+      const unsigned long long a0 = keys[2 * t], a1 = keys[2 * t + 1];
+      k0 = a0 > k0 ? a0 : k0;
+      k1 = a1 > k1 ? a1 : k1;
+    }
+    k0 = warp_max_u64(k0);
+    k1 = warp_max_u64(k1);
+    if (lane == 0) { red0[warp] = k0; red1[warp] = k1; }
+    if (tid == 0) sh_nlist = 0;
+    __syncthreads();
+    if (warp == 0) {
+      k0 = warp_max_u64(red0[lane]);
+      k1 = warp_max_u64(red1[lane]);
+      if (lane == 0) { sh_best[0] = k0; sh_best[1] = k1; }
+    }
+    __syncthreads();
+    const unsigned long long b0 = sh_best[0], b1 = sh_best[1];
+    if (b0 == 0ull || b1 == 0ull) {                  // no selectable node on one side (cKL.cpp:387-389)
+      if (tid == 0) sh_done = 1;
+      __syncthreads();
+      break;
+    }
+    KL_PHASE(0);
+    ++it_local;
+    const uint32_t ia = 0xFFFFFFFFu - (uint32_t)(b0 & 0xFFFFFFFFull), ib = 0xFFFFFFFFu - (uint32_t)(b1 & 0xFFFFFFFFull);
+    const int32_t a = ASC ? (int32_t)ia : __ldg(p.order0 + ia);
+    const int32_t b = ASC ? (int32_t)ib : __ldg(p.order1 + ib);
+    const int32_t alo = __ldg(p.rowptr + a), ahi = __ldg(p.rowptr + a + 1);
+    const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
+    const int32_t da = ahi - alo, items = da + (bhi - blo);
+    KL_PHASE(1);
+    constexpr int WORKERS = KL_LOOP_THREADS / 32 - 1;    // warp 31 is the bookkeeper
+    const uint32_t stamp = it_local;
+    if (warp == WORKERS) {
+      // ---- S2 (off the critical path): gain, cut, trace, termination, lock-and-swap ----
+      float wab = 0.0f;
+      for (int32_t i = alo + lane; i < ahi; i += 32)
+        if (__ldg(p.col + i) == b) wab = __ldg(p.w + i);             // getEdgeWeight, cKL.cpp:75-82
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wab = fmaxf(wab, __shfl_xor_sync(FULL_MASK, wab, o));   // weights are > 0
+      if (lane == 0) {
+        const float maxGain = float_from_orderable((uint32_t)(b0 >> 32));
+        const float minGain = __fsub_rn(0.0f, float_from_orderable((uint32_t)(b1 >> 32)));
+        const float gain = __fsub_rn(__fsub_rn(maxGain, minGain), __fmul_rn(2.0f, wab));    // cKL.cpp:360
+        const float cut = __fsub_rn(sh_cut, gain);                                          // cKL.cpp:362
+        sh_cut = cut;
+        sh_iter = it_local;
+        p.t_cut[it_local] = cut; p.t_gain[it_local] = gain; p.t_n1[it_local] = a; p.t_n2[it_local] = b;
+        p.state[a] = (uint8_t)(ST_SIDE | ST_LOCK);                   // swip, cKL.cpp:274-286
+        p.state[b] = (uint8_t)(ST_LOCK);
+        // the workers take a's and b's sides from (a, b) directly, never from these words
+        bits[a >> 4] = (bits[a >> 4] & ~(3u << ((a & 15) * 2))) | ((ST_SIDE | ST_LOCK) << ((a & 15) * 2));
+        bits[b >> 4] = (bits[b >> 4] & ~(3u << ((b & 15) * 2))) | (ST_LOCK << ((b & 15) * 2));
+        // a and b held the best keys of their tiles: those tiles are rescanned
+        if (atomicExch(stamps + a / KL_TILE, stamp) != stamp) list[atomicAdd(&sh_nlist, 1)] = a / KL_TILE;
+        if (atomicExch(stamps + b / KL_TILE, stamp) != stamp) list[atomicAdd(&sh_nlist, 1)] = b / KL_TILE;
+        if (gain <= 0.0f) { if (++sh_term > p.term_limit) sh_done = 1; }   // cKL.cpp:382-386
+        else sh_term = 0;
+        if (--sh_rem0 == 0) sh_done = 1;
+        if (--sh_rem1 == 0) sh_done = 1;
+      }
+    } else {
+      // ---- S3: recompute D of every neighbour of a or b from scratch (cKL.cpp:253-272) ----
+      // lane k holds the warp's k-th neighbour (id, row extent, rank): ONE round trip for all of them; then the
+      // first 32 entries of four rows at a time are in flight before the first row is summed
+      const int32_t n_mine = items > warp ? (items - 1 - warp) / WORKERS + 1 : 0;
+      for (int32_t k0i = 0; k0i < n_mine; k0i += 32) {
+        int32_t my_v = 0;
+        int2 my_ext = make_int2(0, 0);
+        const int32_t kidx = k0i + lane;
+        if (kidx < n_mine) {
+          const int32_t it = warp + kidx * WORKERS;
+          const int32_t e = it < da ? alo + it : blo + (it - da);
+          my_v = __ldg(p.col + e);
+          my_ext = __ldg(p.nb + e);
+        }
+        uint32_t my_id = (uint32_t)my_v;
+        if (!ASC && kidx < n_mine) my_id = __ldg(p.rank + my_v);
+        const int cnt = min(32, n_mine - k0i);
+        for (int j0 = 0; j0 < cnt; j0 += 4) {
+          int32_t lo[4], hi[4], c[4];
+          float ww[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int j = min(j0 + u, cnt - 1);
+            lo[u] = __shfl_sync(FULL_MASK, my_ext.x, j);
+            hi[u] = __shfl_sync(FULL_MASK, my_ext.y, j);
+            if (j0 + u >= cnt) hi[u] = lo[u];
+            c[u] = 0; ww[u] = 0.0f;
+            if (lo[u] + lane < hi[u]) { c[u] = __ldg(p.col + lo[u] + lane); ww[u] = __ldg(p.w + lo[u] + lane); }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            if (j0 + u < cnt) {                                    // warp-uniform
+              const int32_t v = __shfl_sync(FULL_MASK, my_v, j0 + u);
+              const uint32_t vid = __shfl_sync(FULL_MASK, my_id, j0 + u);
+              const float nv = warp_row_value_local(p.col, p.w, bits, lo[u], hi[u], a, b, lane, c[u], ww[u]);
+              if (lane == 0) {
+                __stcg(p.val + v, nv);
+                const unsigned st = bits_get(bits, v);
+                if (!(st & ST_LOCK) && v != a && v != b) {
+                  // the tile's key: raised in place, unless v itself held it (then the tile is rescanned)
+                  const int32_t tile = v / KL_TILE;
+                  unsigned long long *kp = keys + 2 * tile + (st & ST_SIDE);
+                  const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+                  if (cur != 0ull && (uint32_t)(cur & 0xFFFFFFFFull) == 0xFFFFFFFFu - vid) {
+                    if (atomicExch(stamps + tile, stamp) != stamp) list[atomicAdd(&sh_nlist, 1)] = tile;
+                  } else {
+                    atomicMax(kp, kl_key<ASC>(nv, st & ST_SIDE, vid));
+                  }
+                }
+              }
+            }
+          }
+        }
+      }
+    }
+    KL_PHASE(2);
+    __syncthreads();
+    KL_PHASE(3);
+    // ---- S4: rescan the few tiles whose best node was touched or locked, one per warp ----
+    {
+      const int nl = sh_nlist;
+      for (int q = warp; q < nl; q += KL_LOOP_THREADS / 32) tile_scan_local<ASC>(bits, p.val, p.rank, p.n, list[q], lane, keys);
+    }
+    KL_PHASE(4);
+    __syncthreads();
+    KL_PHASE(5);
+  }
+  if (tid == 0) {
+    p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1;
+#ifdef EIGKL_KL_CLOCKS
+    for (int i = 0; i < 6; ++i) p.ctrl[8 + i] = tph[i];
+#endif
+  }
+#undef KL_PHASE
+}
+
 void kl_run(eigkl_handle *h) {
   auto &A = h->A;
   auto &k = h->kl;
@@ -644,8 +942,17 @@ void kl_run(eigkl_handle *h) {
   const int R = h->opts.nranks;
   int32_t own_lo = 0, own_hi = n, own_pad = 0;
   if (R > 1) row_partition(n, R, h->opts.rank, &own_lo, &own_hi, &own_pad);
-  tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, own_lo, own_hi, n_tiles, k.tile_key.p, k.tile_stamp.p);
-  h->launches++;
+  // state in shared memory (one CTA) whenever it fits, unless a cluster size was asked for explicitly
+  const bool local = R == 1 && h->kl_local && h->opts.kl_cluster <= 0 && n <= KL_LOCAL_MAX_N;
+  if (!local) {
+    tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, own_lo, own_hi, n_tiles, k.tile_key.p, k.tile_stamp.p);
+    h->launches++;
+  } else if (!A.nb_valid) {
+    A.nb.alloc((size_t)2 * A.nnz + 2);
+    nb_extent_kernel<<<grid_for(A.nnz), TPB, 0, st>>>(A.rowptr.p, A.col.p, A.nnz, reinterpret_cast<int2 *>(A.nb.p));
+    h->launches++;
+    A.nb_valid = true;
+  }
   const float zero = 0.0f; const int32_t neg = -1;
   EIGKL_CUDA(cudaMemcpyAsync(k.t_cut.p, &cut0, sizeof(float), cudaMemcpyHostToDevice, st));
   EIGKL_CUDA(cudaMemcpyAsync(k.t_gain.p, &zero, sizeof(float), cudaMemcpyHostToDevice, st));
@@ -689,7 +996,27 @@ void kl_run(eigkl_handle *h) {
   attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   h->timer.start(st);
-  if (R == 1) {
+  if (local) {
+    KlLocalParams q;
+    q.n = n; q.n_tiles = n_tiles;
+    q.rowptr = A.rowptr.p; q.col = A.col.p; q.nb = reinterpret_cast<const int2 *>(A.nb.p); q.w = A.w.p;
+    q.state = k.state.p; q.rank = k.rank.p; q.val = k.val.p; q.order0 = k.order0.p; q.order1 = k.order1.p;
+    q.t_cut = k.t_cut.p; q.t_gain = k.t_gain.p; q.t_n1 = k.t_n1.p; q.t_n2 = k.t_n2.p;
+    q.ctrl = k.ctrl.p; q.cut0 = cut0; q.term_limit = p.term_limit; q.n0 = k.n0; q.n1 = k.n1;
+    const size_t smem = (size_t)n_tiles * (16 + 4 + 4) + (size_t)((n + 15) / 16) * 4 + 16;
+    static bool configured = false;
+    if (!configured) {
+      const size_t max_smem = (size_t)(KL_LOCAL_MAX_N / KL_TILE) * 24 + (size_t)(KL_LOCAL_MAX_N / 16) * 4 + 16;
+      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      configured = true;
+    }
+    nc = 1;
+    if (k.ascending) kl_loop_local_kernel<true><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+    else kl_loop_local_kernel<false><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+    EIGKL_CUDA(cudaGetLastError());
+    h->launches++;
+  } else if (R == 1) {
     EIGKL_CUDA(cudaLaunchKernelEx(&cfg, kl_loop_kernel<false>, p));
     h->launches++;
   } else {
@@ -734,6 +1061,7 @@ void kl_run(eigkl_handle *h) {
   }
   h->stats.kl_cluster = nc;
   h->stats.kl_threads = nc * KL_LOOP_THREADS;
+  h->stats.kl_local = local ? 1 : 0;
 }
 
 }  // namespace eigkl

@@ -93,6 +93,8 @@ typedef struct {
    * n_multidot / ms_multidot; n_update stays 0), 0 when they are separate multidot/update launches */
   int32_t  gs_fused;
   int32_t  gs_cache_cols;        /* basis columns the fused kernel keeps in shared memory            */
+  int32_t  kl_local;             /* 1: the swap loop ran as one CTA with tile keys and side bits in shared memory */
+  int32_t  reserved0;
 } eigkl_stats;
 
 /* KL trace, one row per swap plus row 0 (the initial cut) -- the rows cKL writes to
