@@ -315,6 +315,7 @@ void fiedler_solve(eigkl_handle *h);
 void partition_from_fiedler(eigkl_handle *h);
 void sym_eig(int n, double *a, double *evals);   // dense symmetric eigen-solver (host)
 void tridiag_top_eig(int n, const double *d, const double *e, int k, double *theta, double *Y);   // k largest pairs
+void sym_top_eig(int n, const double *a, int k, double *theta, double *Y);   // k largest pairs of a dense symmetric matrix
 
 // ---- KL (kl.cu) ---------------------------------------------------------------------------------------
 void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *order0, int64_t n0,

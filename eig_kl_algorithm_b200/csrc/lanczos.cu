@@ -866,14 +866,10 @@ void fiedler_solve(eigkl_handle *h) {
         T[(size_t)j * m + j] = alpha[j];
         if (j + 1 < m) { T[(size_t)j * m + j + 1] = beta[j]; T[(size_t)(j + 1) * m + j] = beta[j]; }
       }
-      std::vector<double> A((size_t)jj * jj), ev(jj);
+      std::vector<double> A((size_t)jj * jj);
       for (int r = 0; r < jj; ++r)
         for (int q = 0; q < jj; ++q) A[(size_t)r * jj + q] = T[(size_t)r * m + q];
-      sym_eig(jj, A.data(), ev.data());
-      for (int t = 0; t < 2; ++t) {
-        th_top[t] = ev[jj - 1 - t];
-        for (int r = 0; r < jj; ++r) Ytop[(size_t)t * jj + r] = A[(size_t)r * jj + (jj - 1 - t)];
-      }
+      sym_top_eig(jj, A.data(), 2, th_top, Ytop.data());
     }
     int nconv = 0;
     for (int t = 0; t < nev; ++t) {
@@ -984,18 +980,16 @@ void fiedler_solve(eigkl_handle *h) {
         if (j + 1 < m) { T[(size_t)j * m + j + 1] = beta[j]; T[(size_t)(j + 1) * m + j] = beta[j]; }
       }
       const double beta_m = beta[m - 1];
-      Yh = T;
-      sym_eig(m, Yh.data(), theta.data());
       int kk = h->opts.keep > 0 ? h->opts.keep : std::max(nev + 1, m / 5);
       kk = std::max(nev, std::min(kk, m - 2));
+      // only the kk kept pairs are needed (descending): Ycm column cc = cc-th largest Ritz vector
+      Ycm.assign((size_t)m * kk, 0.0);
+      sym_top_eig(m, T.data(), kk, theta.data(), Ycm.data());
       // v_m = w / beta_m into column m
       if (c.nl > 0) {
         scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[cur].p, e.scal.p + 1, V + (size_t)m * c.ld, c.nl);
         h->launches++;
       }
-      Ycm.assign((size_t)m * kk, 0.0);
-      for (int cc = 0; cc < kk; ++cc)
-        for (int j = 0; j < m; ++j) Ycm[(size_t)cc * m + j] = Yh[(size_t)j * m + (m - 1 - cc)];
       EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), Ycm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
       double *Vn = e.V[bank ^ 1].p;
       if (c.nl > 0) {
@@ -1009,8 +1003,8 @@ void fiedler_solve(eigkl_handle *h) {
       EIGKL_CUDA(cudaStreamSynchronize(st));    // Ycm is reused
       std::fill(T.begin(), T.end(), 0.0);
       for (int cc = 0; cc < kk; ++cc) {
-        T[(size_t)cc * m + cc] = theta[m - 1 - cc];
-        const double sv = beta_m * Yh[(size_t)(m - 1) * m + (m - 1 - cc)];
+        T[(size_t)cc * m + cc] = theta[cc];
+        const double sv = beta_m * Ycm[(size_t)cc * m + (m - 1)];
         T[(size_t)kk * m + cc] = sv;
         T[(size_t)cc * m + kk] = sv;
       }

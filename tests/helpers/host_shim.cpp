@@ -37,6 +37,9 @@ int shim_read_eig(const char *path, int32_t n, uint8_t *side, char *err, int err
 int shim_sym_eig(int n, double *a, double *evals) {
   try { sym_eig(n, a, evals); return 0; } catch (const Error &e) { return e.code; }
 }
+int shim_sym_top_eig(int n, const double *a, int k, double *theta, double *Y) {
+  try { sym_top_eig(n, a, k, theta, Y); return 0; } catch (const Error &e) { return e.code; }
+}
 int shim_tridiag_top(int n, const double *d, const double *e, int k, double *theta, double *Y) {
   try { tridiag_top_eig(n, d, e, k, theta, Y); return 0; } catch (const Error &e2) { return e2.code; }
 }

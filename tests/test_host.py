@@ -109,6 +109,35 @@ def test_dense_eig(shim, n):
     assert np.abs(z.T @ z - np.eye(n)).max() < 1e-12 * n
 
 
+@pytest.mark.parametrize("n,keep,shape", [(100, 20, "arrow"), (100, 20, "tridiag"), (37, 7, "arrow"), (30, 5, "dense"), (6, 2, "arrow")])
+def test_sym_top_eig(shim, n, keep, shape):
+    """The k largest pairs of the projected matrix of a thick-restart cycle (what the restart and the convergence
+    check need) by Householder (skipping rows already tridiagonal) + bisection + inverse iteration, vs numpy."""
+    rng = np.random.default_rng(7 * n + keep)
+    a = np.zeros((n, n))
+    if shape == "dense":
+        b = rng.standard_normal((n, n))
+        a = b + b.T
+    else:
+        kk = keep if shape == "arrow" else 0
+        a[np.arange(n), np.arange(n)] = np.sort(np.abs(rng.standard_normal(n)) * np.logspace(3, 0, n))[::-1]
+        if kk:
+            a[kk, :kk] = a[:kk, kk] = rng.standard_normal(kk) * 1e-2
+        for j in range(kk, n - 1):
+            a[j, j + 1] = a[j + 1, j] = abs(rng.standard_normal()) + 0.05
+    th = np.zeros(keep)
+    Y = np.zeros(n * keep)
+    shim.shim_sym_top_eig.restype = C.c_int
+    assert shim.shim_sym_top_eig(C.c_int(n), _p(np.ascontiguousarray(a), C.c_double), C.c_int(keep), _p(th, C.c_double), _p(Y, C.c_double)) == 0
+    w, V = np.linalg.eigh(a)
+    scale = np.abs(w).max()
+    assert np.allclose(th, w[::-1][:keep], atol=1e-12 * scale)
+    Y = Y.reshape(keep, n).T
+    assert np.abs(Y.T @ Y - np.eye(keep)).max() < 1e-10
+    for t in range(keep):
+        assert np.linalg.norm(a @ Y[:, t] - th[t] * Y[:, t]) < 1e-11 * scale
+
+
 @pytest.mark.parametrize("n", [2, 3, 10, 37, 100])
 def test_tridiag_top_eig(shim, n):
     """Top-k pairs of a Lanczos-like tridiagonal (bisection + inverse iteration) vs numpy."""
