@@ -372,7 +372,13 @@ def main():
         kernels["restart"] = cls("restart", bytes_total=(s1["n_restart"] - s0["n_restart"]) * (s1["ncv"] + max(3, s1["ncv"] // 5)) * n_nodes * 8.0)
         kernels["dvalues"] = cls("dvalues", bytes_each=s1["bytes_dvalues"])
         kernels["kl_loop"] = {"launches": 1, "ms_total": s1["ms_kl_loop"], "swaps": s1["kl_swaps"],
-                              "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]), "bound": "latency (cluster barriers), not bandwidth"}
+                              "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]),
+                              "state_in_shared_memory": bool(s1.get("kl_local", 0)),
+                              "bound": "latency (a chain of dependent L2 round trips per swap), not bandwidth"}
+        if kernels.get("multidot") and s1.get("gs_fused", 0):
+            kernels["multidot"]["note"] = ("fused Gram-Schmidt: ONE cooperative launch per Lanczos step does both passes "
+                                           "(h1, update, h2, update, DGKS decision, norm); %d basis columns cached in shared memory; "
+                                           "algorithmic bytes = the basis once + w in and out" % int(s1.get("gs_cache_cols", 0)))
         kernels["spmv_isolated"] = {"us_avg_l2_warm": spmv_iso * 1e3, "us_avg_l2_flushed": spmv_cold * 1e3,
                                     "gbs_l2_warm": s1["bytes_spmv"] / (spmv_iso * 1e-3) / 1e9,
                                     "gbs_l2_flushed": s1["bytes_spmv"] / (spmv_cold * 1e-3) / 1e9}

@@ -315,13 +315,13 @@ struct ResidentArgs {
 // so a CTA can only publish y_{k+1} after every CTA that reads its rows has published y_k, i.e. has already
 // consumed its y_{k-1}, the value being overwritten.
 __device__ __forceinline__ void ll_store(uint4 *p, double v, uint32_t tag) {
-  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)__double2loint(v)), "r"(tag),
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((uint32_t)__double2loint(v)), "r"(tag),
                "r"((uint32_t)__double2hiint(v)), "r"(tag)
                : "memory");
 }
 __device__ __forceinline__ uint4 ll_load(const uint4 *p) {
   uint4 v;
-  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+  asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
   return v;
 }
 
