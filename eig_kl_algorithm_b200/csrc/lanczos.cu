@@ -4,21 +4,26 @@
 // SmallestAlge, tol 1e-10, maxit 1000): the two algebraically smallest eigenpairs of the clique
 // Laplacian, of which the larger (lambda2, Fiedler vector) is reported.
 //
-// Device side, one Lanczos step j (all on one stream, no host round trip inside a restart cycle):
-//   spmv      w' = L (w / beta_{j-1}),  v_j = w / beta_{j-1} stored by the same kernel      (spmv.cu)
-//   multidot  h  = V_{0..j}^T w'        column groups x row chunks, warp-shuffle + block reduce,
-//                                       last finishing CTA folds the partials in a fixed order
-//   update    w' -= V_{0..j} h          one row per thread, coalesced across the basis columns
-//   multidot, update again              ("twice is enough" full re-orthogonalisation), the second
-//                                       update also reduces |w'|^2 -> beta_j, 1/beta_j
-// Host side, once per cycle: ncv alphas/betas come back, the small projected eigenproblem is solved
-// (dense_eig.cpp), convergence is tested as |beta_m y_last| < tol * max(eps^(2/3), |theta|) for
-// both wanted pairs, and the basis is compressed to `keep` Ritz vectors by one tall-skinny
-// V <- V Y kernel (restart).
+// Device side, one Lanczos step j (all on one stream; the host only reads alpha/beta back at the checks).
+// The operator is the Chebyshev filter B = T_d(L) (see fiedler_solve), applied as d SpMVs.
+//   * single rank, matrix fits the chip: TWO cooperative launches per step --
+//       cheb_resident_kernel  w' = B (w / beta_{j-1}), v_j stored                            (spmv.cu)
+//       gs_fused_kernel       both Gram-Schmidt passes, DGKS decision, alpha_j, beta_j, 1/beta_j
+//   * otherwise (multi-rank, or too large): one launch per SpMV (spmv_flat/adaptive_kernel, chained with
+//     programmatic dependent launches) and
+//       multidot  h  = V_{0..j}^T w'        column groups x row chunks, warp-shuffle + block reduce,
+//                                           last finishing CTA folds the partials in a fixed order
+//       update    w' -= V_{0..j} h          one row per thread, coalesced across the basis columns
+//       multidot, update again              second pass when the DGKS test asks for it
+// Host side: every 4 steps (tridiagonal T) or at cycle ends the two largest Ritz pairs of the projected
+// matrix are computed (dense_eig.cpp: bisection + inverse iteration), convergence is tested on
+// |beta_m y_last|, and at a cycle end the basis is compressed to `keep` Ritz vectors by one tall-skinny
+// V <- V Y kernel (thick restart).
 // Every reduction runs in a fixed order, so results are bit-reproducible run to run.
-// Bound: HBM/L2 bandwidth; the re-orthogonalisation streams 4*j*n*8 bytes per step, the SpMV
-// nnz*12 + n*20.  No dense contraction worth a tensor core: the only GEMM-shaped piece is the
-// n x ncv by ncv x keep restart, run once per ~80 steps.
+// Bound: on the shipped circuits latency (dependent L2 round trips, SM-to-SM hand-offs); at 2 M nodes HBM
+// bandwidth -- the re-orthogonalisation streams up to 4*j*n*8 bytes per step, the SpMV nnz*12 + n*20.
+// No dense contraction worth a tensor core: the only GEMM-shaped piece is the n x ncv by ncv x keep
+// restart, run once per ~80 steps.
 #include "internal.h"
 #include "device_utils.cuh"
 #include <algorithm>

@@ -3,8 +3,13 @@
 // Replaces Spectra's SparseSymMatProd (cEIG.cpp:194, serial Eigen product) and is the B200 answer to
 // the reference's only GPU SpMV, sparseMVKernel (gKL2.cu:65-89: thread-per-row, scalar, fp32).
 //
+// Three kernels, chosen per matrix at assembly:
+//   cheb_resident_kernel  (single rank, the matrix fits the chip's registers + shared memory): a whole filter
+//                         application, d SpMVs, per launch -- see "Resident polynomial filter" below;
+//   spmv_flat_kernel      one launch per SpMV, the whole row block in one round of loads (default otherwise);
+//   spmv_adaptive_kernel  one launch per SpMV, lanes-per-row chosen per block (EIGKL_SPMV_MODE = 1 / 2).
 // Layout: CSR with int32 rowptr/col and fp64 values, rows cut into row blocks of ~SPMV_CHUNK
-// non-zeros (blk_row, built at assembly).  One CTA per row block:
+// non-zeros (blk_row, built at assembly).  spmv_adaptive_kernel, one CTA per row block:
 //   * stream mode (very short rows, mean < 4 entries): all threads stream val/col fully coalesced,
 //     gather x through the read-only path, stage the products in shared memory, then 1..32 threads
 //     per row reduce each row from shared memory;
