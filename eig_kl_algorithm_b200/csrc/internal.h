@@ -227,6 +227,7 @@ struct EigState {
   DBuf<double> scal;           // [0] norm^2, [1] 1/beta, ...
   DBuf<unsigned int> counters; // last-block-done counters
   DBuf<int> flag;              // [0] = 1: second Gram-Schmidt pass of the current step is skipped
+  HBuf<double> snap;           // pinned snapshot of alpha / beta for the deferred convergence checks
   DBuf<double> gs_partial;     // fused Gram-Schmidt kernel: per-CTA partial dot products / norms
   DBuf<unsigned int> gs_sync;  // [0] grid-barrier arrivals (monotonic within a solve), [1] last-CTA ticket
   DBuf<double> Y;              // ncv*ncv restart coefficients (column major, ld = ncv)

@@ -856,11 +856,9 @@ void fiedler_solve(eigkl_handle *h) {
   std::vector<double> Ytop;                  // (jfin+1) x 2, column-major: the two wanted Ritz vectors in the basis
   double th_top[2] = {0, 0};
 
-  // convergence test on the leading (jj x jj) block after step jj-1; fills Ytop / th_top
-  auto check = [&](int jj) -> bool {
-    EIGKL_CUDA(cudaMemcpyAsync(alpha.data(), e.alpha.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EIGKL_CUDA(cudaMemcpyAsync(beta.data(), e.beta.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
-    EIGKL_CUDA(cudaStreamSynchronize(st));
+  // convergence test on the leading (jj x jj) block after step jj-1 (alpha / beta already on the host);
+  // fills Ytop / th_top
+  auto evaluate = [&](int jj) -> bool {
     beta_last = beta[jj - 1];
     EIGKL_REQUIRE(std::isfinite(beta_last), EIGKL_E_NOCONV, "eigkl_fiedler: Lanczos breakdown (non-finite beta)");
     Ytop.assign((size_t)jj * 2, 0.0);
@@ -882,6 +880,38 @@ void fiedler_solve(eigkl_handle *h) {
       if (res[t] < tol_p * std::max(std::fabs(th_top[t]), 1.0)) ++nconv;
     }
     return nconv == nev;
+  };
+  // blocking form (cycle ends): the stream is drained, the host decides, the GPU waits
+  auto check = [&](int jj) -> bool {
+    EIGKL_CUDA(cudaMemcpyAsync(alpha.data(), e.alpha.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EIGKL_CUDA(cudaMemcpyAsync(beta.data(), e.beta.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EIGKL_CUDA(cudaStreamSynchronize(st));
+    return evaluate(jj);
+  };
+  // deferred form (the checks inside the first cycle): alpha / beta are snapshot into pinned memory behind
+  // step jj, the NEXT step is enqueued, and only then does the host wait for the snapshot and run the small
+  // eigenproblem -- while the GPU works on that next step instead of idling through a stream drain, the host
+  // arithmetic and two launch latencies (24 such checks on ibm10: ~1 ms).  A positive check is acted on one
+  // step late (the extra basis column is simply not used).  The lag is fixed, so every rank decides alike.
+  struct EvGuard { cudaEvent_t ev = nullptr; ~EvGuard() { if (ev) cudaEventDestroy(ev); } } chk;
+  EIGKL_CUDA(cudaEventCreateWithFlags(&chk.ev, cudaEventDisableTiming));
+  e.snap.ensure(2 * (size_t)m);
+  int pend_jj = 0;                           // 0: no snapshot in flight
+  const bool defer_checks = !getenv("EIGKL_SYNC_CHECKS");
+  auto post_check = [&](int jj) {
+    EIGKL_CUDA(cudaMemcpyAsync(e.snap.p, e.alpha.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EIGKL_CUDA(cudaMemcpyAsync(e.snap.p + m, e.beta.p, (size_t)jj * sizeof(double), cudaMemcpyDeviceToHost, st));
+    EIGKL_CUDA(cudaEventRecord(chk.ev, st));
+    pend_jj = jj;
+  };
+  auto harvest = [&]() -> int {
+    if (!pend_jj) return 0;
+    EIGKL_CUDA(cudaEventSynchronize(chk.ev));
+    const int jj = pend_jj;
+    pend_jj = 0;
+    std::copy(e.snap.p, e.snap.p + jj, alpha.begin());
+    std::copy(e.snap.p + m, e.snap.p + m + jj, beta.begin());
+    return jj;
   };
 
   // Rayleigh-Ritz on L over the two Ritz vectors; returns the true residual of the Fiedler pair
@@ -964,15 +994,25 @@ void fiedler_solve(eigkl_handle *h) {
       orthogonalise(c, V, j, e.w[cur].p);
       const int jj = j + 1;
       const bool at_end = (jj == m);
-      const bool do_check = at_end || (k == 0 && jj >= 8 && jj % check_every == 0);
-      if (do_check && check(jj)) {
-        jfin = j;
-        true_res = extract(jj);
-        // accept when the pair is a genuine eigenpair of L (the reference's criterion is the same
-        // relative 1e-10 on its own Ritz estimate); otherwise tighten the filtered tolerance and go on
+      // accept when the pair is a genuine eigenpair of L (the reference's criterion is the same
+      // relative 1e-10 on its own Ritz estimate); otherwise tighten the filtered tolerance and go on
+      auto positive = [&](int cj) {
+        jfin = cj - 1;
+        true_res = extract(cj);
         const double accept = std::max(1e-9 * std::fabs(lam2), 1e-13 * fb);
         if (true_res <= accept || tol_p < 1e-15) { converged = true; cycle_done = true; }
         else tol_p *= 1e-2;
+      };
+      if (const int pj = harvest()) {        // the check posted behind the previous step
+        if (evaluate(pj)) positive(pj);
+      }
+      if (!converged) {
+        const bool mid = (k == 0 && jj >= 8 && jj % check_every == 0);
+        if (at_end || (mid && !defer_checks)) {
+          if (check(jj)) positive(jj);
+        } else if (mid) {
+          post_check(jj);
+        }
       }
       if (at_end) cycle_done = true;
     }
