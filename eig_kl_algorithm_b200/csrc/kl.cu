@@ -669,33 +669,42 @@ constexpr int32_t KL_LOCAL_MAX_N = 524288;
 
 __device__ __forceinline__ unsigned bits_get(const uint32_t *bits, int32_t u) { return (bits[u >> 4] >> ((u & 15) * 2)) & 3u; }
 
-// as warp_row_value, sides from the shared-memory bits; (c, ww) = this lane's entry of the row's first 32, already loaded
+// as warp_row_value, sides from the shared-memory bits; (c, ww) = this lane's entry of the row's first 32, already
+// loaded.  The two ordered sums are independent chains -- E only ever grows by the external weights, I by the
+// internal ones (the other accumulator gets + 0.0f, which changes nothing) -- so the weights are compacted in row
+// order into two per-warp lists (ballot + popc) and lane 0 adds the E list while lane 1 adds the I list: the
+// same additions in the same order, in max(#E, #I) steps of LDS + FADD instead of 32 steps of shuffle + two
+// FMNMX + two FADD executed by the whole warp (ncu: that replay was ~70% of the loop's 17 K warp instructions
+// per swap, on a kernel whose issue slots are 41% busy).
 __device__ __forceinline__ float warp_row_value_local(const int32_t *__restrict__ col, const float *__restrict__ w,
                                                       const uint32_t *bits, int32_t lo, int32_t hi, int32_t ov_a, int32_t ov_b,
-                                                      int lane, int32_t c, float ww) {
-  float E = 0.0f, I = 0.0f;
+                                                      int lane, int32_t c, float ww, float *wsm /* 64 floats of this warp */) {
+  float acc = 0.0f;                                  // lane 0: E, lane 1: I
+  const unsigned lt = (1u << lane) - 1u;
   for (int32_t base = lo; base < hi; base += 32) {
     const bool valid = (base + lane) < hi;
     int32_t cn = 0;
     float wn = 0.0f;
     const int32_t in = base + 32 + lane;
     if (in < hi) { cn = __ldg(col + in); wn = __ldg(w + in); }   // next 32 entries while this chunk is summed
-    float x = 0.0f;
+    bool ext = false;
     if (valid) {
-      unsigned sd;
-      if (c == ov_a) sd = 1u;
-      else if (c == ov_b) sd = 0u;
-      else sd = bits_get(bits, c) & ST_SIDE;
-      x = sd ? ww : -ww;
+      if (c == ov_a) ext = true;
+      else if (c == ov_b) ext = false;
+      else ext = (bits_get(bits, c) & ST_SIDE) != 0u;
     }
-    const int cnt = min(32, hi - base);
-    for (int t = 0; t < cnt; ++t) {
-      const float xt = __shfl_sync(FULL_MASK, x, t);
-      E = __fadd_rn(E, fmaxf(xt, 0.0f));
-      I = __fadd_rn(I, fmaxf(-xt, 0.0f));
+    const unsigned P = __ballot_sync(FULL_MASK, valid && ext), N = __ballot_sync(FULL_MASK, valid && !ext);
+    if (valid) wsm[ext ? __popc(P & lt) : 32 + __popc(N & lt)] = ww;
+    __syncwarp();
+    if (lane < 2) {
+      const float *src = wsm + 32 * lane;
+      const int cnt = __popc(lane ? N : P);
+      for (int t = 0; t < cnt; ++t) acc = __fadd_rn(acc, src[t]);
     }
+    __syncwarp();
     c = cn; ww = wn;
   }
+  const float E = __shfl_sync(FULL_MASK, acc, 0), I = __shfl_sync(FULL_MASK, acc, 1);
   return __fsub_rn(E, I);
 }
 
@@ -768,6 +777,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   __shared__ unsigned long long red0[32], red1[32];
   __shared__ unsigned long long sh_best[2];
+  __shared__ float sh_wsm[KL_LOOP_THREADS / 32][64];   // per warp: the E and I weight lists of the row being summed
   __shared__ float sh_cut;
   __shared__ uint32_t sh_term, sh_iter;
   __shared__ int sh_done, sh_nlist;
@@ -900,7 +910,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
             if (j0 + u < cnt) {                                    // warp-uniform
               const int32_t v = __shfl_sync(FULL_MASK, my_v, j0 + u);
               const uint32_t vid = __shfl_sync(FULL_MASK, my_id, j0 + u);
-              const float nv = warp_row_value_local(p.col, p.w, bits, lo[u], hi[u], a, b, lane, c[u], ww[u]);
+              const float nv = warp_row_value_local(p.col, p.w, bits, lo[u], hi[u], a, b, lane, c[u], ww[u], sh_wsm[warp]);
               if (lane == 0) {
                 __stcg(p.val + v, nv);
                 const unsigned st = bits_get(bits, v);
