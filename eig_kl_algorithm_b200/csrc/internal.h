@@ -265,6 +265,9 @@ struct eigkl_handle {
   int spmv_pdl = 1;            // EIGKL_SPMV_PDL=0 disables programmatic dependent launch of the SpMV chain
   int spmv_resident = 1;       // EIGKL_SPMV_RESIDENT=0: one launch per SpMV even when the matrix fits on chip
   int gs_fused = 1;            // EIGKL_GS_FUSED=0: Gram-Schmidt as separate multidot / update launches
+  // per-handle (= per-device) one-time kernel attribute set-up, and what the device allows
+  bool attr_kl_local = false, attr_gs = false, attr_resident = false;
+  int coop_ok = -1;            // -1 unknown, 0/1: cudaDevAttrCooperativeLaunch
   int kl_local = 1;            // EIGKL_KL_LOCAL=0: never run the swap loop with its state in shared memory
   int coop_launch = 1;         // EIGKL_COOP=0: launch the grid-synchronising kernels without the cooperative attribute (tuning aid)
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
@@ -306,6 +309,7 @@ void spmv_launch(eigkl_handle *h, const double *x, double *y, const double *scal
 bool cheb_resident_usable(const eigkl_handle *h);
 void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *scale, double *v_store, double *const w[3],
                           const unsigned char *out_idx, int deg, double fc, double fe);
+bool device_cooperative(eigkl_handle *h);        // lanczos.cu
 void spmv_resident_print_phases();
 void cheb_resident_plan(eigkl_handle *h);          // enqueue (no sync)
 void cheb_resident_plan_finish(eigkl_handle *h);   // after the stream has been synchronised

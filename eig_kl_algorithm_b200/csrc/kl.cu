@@ -1032,12 +1032,11 @@ void kl_run(eigkl_handle *h) {
     q.t_cut = k.t_cut.p; q.t_gain = k.t_gain.p; q.t_n1 = k.t_n1.p; q.t_n2 = k.t_n2.p;
     q.ctrl = k.ctrl.p; q.cut0 = cut0; q.term_limit = p.term_limit; q.n0 = k.n0; q.n1 = k.n1;
     const size_t smem = (size_t)n_tiles * (16 + 4 + 4) + (size_t)((n + 15) / 16) * 4 + 16;
-    static bool configured = false;
-    if (!configured) {
+    if (!h->attr_kl_local) {
       const size_t max_smem = (size_t)(KL_LOCAL_MAX_N / KL_TILE) * 24 + (size_t)(KL_LOCAL_MAX_N / 16) * 4 + 16;
       EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
       EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-      configured = true;
+      h->attr_kl_local = true;
     }
     nc = 1;
     if (k.ascending) kl_loop_local_kernel<true><<<1, KL_LOOP_THREADS, smem, st>>>(q);

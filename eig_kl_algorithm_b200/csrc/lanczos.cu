@@ -582,6 +582,20 @@ struct LzCtx {
   unsigned int gs_base = 0;
 };
 
+}  // namespace
+
+// cooperative launches available on this device? (asked once per handle)
+bool device_cooperative(eigkl_handle *h) {
+  if (h->coop_ok < 0) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, h->device) != cudaSuccess) v = 0;
+    h->coop_ok = v ? 1 : 0;
+  }
+  return h->coop_ok == 1;
+}
+
+namespace {
+
 void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, double *h_out, int pass) {
   auto &e = c.h->eig;
   if (c.nl > 0) {
@@ -794,11 +808,14 @@ void fiedler_solve(eigkl_handle *h) {
       e.gs_partial.ensure((size_t)(2 * m + 8) * c.gs_grid);
       e.gs_sync.ensure(2);
       EIGKL_CUDA(cudaMemsetAsync(e.gs_sync.p, 0, 2 * sizeof(unsigned int), st));
-      static bool gs_configured = false;
-      if (!gs_configured) {
+      if (!h->attr_gs) {
         EIGKL_CUDA(cudaFuncSetAttribute(gs_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
-        gs_configured = true;
+        h->attr_gs = true;
       }
+      // the grid barriers need every CTA resident at once: ask the device, fall back to the separate kernels
+      int per_sm = 0;
+      EIGKL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gs_fused_kernel, GS_THREADS, c.gs_smem));
+      if (!device_cooperative(h) || (int64_t)per_sm * h->sm_count < c.gs_grid) c.gs_fused = false;
     }
   }
   h->stats.gs_fused = c.gs_fused ? 1 : 0;

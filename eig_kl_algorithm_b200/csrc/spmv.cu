@@ -617,16 +617,15 @@ void cheb_resident_plan(eigkl_handle *h) {
   EIGKL_CUDA(cudaMemsetAsync(L.res_ll.p, 0, (size_t)4 * n * sizeof(unsigned long long), h->stream));
   L.res_tag = 0;
   resident_row_blocks(h, chunk);                                   // assemble.cu: res_row, res_info, res_check[0..1]
-  static bool configured = false;
   const size_t plan_smem = ((size_t)2 * ((n + 31) / 32) + 64) * sizeof(uint32_t);
-  if (!configured) {
+  if (!h->attr_resident) {
     EIGKL_CUDA(cudaFuncSetAttribute(res_plan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(((size_t)2 * ((PLAN_MAX_N + 31) / 32) + 64) * sizeof(uint32_t))));
     EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<4, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
     EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<8, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
     EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<16, 768>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
     EIGKL_CUDA(cudaFuncSetAttribute(cheb_resident_kernel<24, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_SMEM));
-    configured = true;
+    h->attr_resident = true;
   }
   res_plan_kernel<<<(unsigned)L.res_blocks, PLAN_THREADS, plan_smem, h->stream>>>(
       L.rowptr.p, L.col.p, reinterpret_cast<const int4 *>(L.res_info.p), n, L.res_src.p, L.res_halo_ids.p, L.res_halo_cnt.p,
