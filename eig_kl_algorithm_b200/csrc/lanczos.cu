@@ -1022,14 +1022,21 @@ void fiedler_solve(eigkl_handle *h) {
         if (true_res <= accept || tol_p < 1e-15) { converged = true; cycle_done = true; }
         else tol_p *= 1e-2;
       };
-      if (const int pj = harvest()) {        // the check posted behind the previous step
+      // a posted check is evaluated `lag` steps later (always by the end of the cycle): one step covers the
+      // tridiagonal solve of the first cycle (~30 us), two cover the arrowhead solve of the later ones (~150 us)
+      const int lag = (k == 0) ? 1 : 2;
+      if (pend_jj && (at_end || jj >= pend_jj + lag)) {
+        const int pj = harvest();
         if (evaluate(pj)) positive(pj);
       }
       if (!converged) {
-        const bool mid = (k == 0 && jj >= 8 && jj % check_every == 0);
-        if (at_end || (mid && !defer_checks)) {
+        // inside a cycle: every check_every steps from the 8th step of the cycle on.  (Before the projected
+        // eigenproblem became cheap and the checks deferred, cycles after a restart were only checked at their
+        // end: ibm10 converged around step 150 of its second cycle and ran on to step 180.)
+        const bool mid = (jj - k >= 8 && (jj - k) % check_every == 0);
+        if (at_end || (mid && !defer_checks && k == 0)) {
           if (check(jj)) positive(jj);
-        } else if (mid) {
+        } else if (mid && defer_checks && !pend_jj) {
           post_check(jj);
         }
       }
