@@ -231,15 +231,38 @@ void tridiag_top_eig(int n, const double *d, const double *e, int k, double *the
   }
   const double tiny = std::max(nrm, 1e-300) * 1e-300 + 2.3e-308 + nrm * 1e-17 * 1e-3;
   std::vector<double> y(n);
-  for (int t = 0; t < k && t < n; ++t) {
-    const int want = n - t;                       // eigenvalue index (1-based, ascending)
-    double a = lo, b = hi;
-    for (int it = 0; it < 200; ++it) {
-      const double mid = 0.5 * (a + b);
-      if (mid <= a || mid >= b) break;
-      if (sturm_count_below(n, d, e, mid, tiny) >= want) b = mid; else a = mid;
+  // bisection for all wanted eigenvalues in lockstep: the Sturm recurrences of the different shifts are
+  // independent chains, so the inner loop over the shifts pipelines / vectorises (the divisions of ONE chain
+  // are a 100-long dependent sequence; 20 values one after the other cost 1.3 ms at n = 100, in lockstep 0.2)
+  const int kw = std::min(k, n);
+  std::vector<double> lo_t(kw, lo), hi_t(kw, hi), mid_t(kw), q_t(kw), e2(n > 1 ? n - 1 : 1);
+  std::vector<int> cnt_t(kw);
+  for (int i = 0; i + 1 < n; ++i) e2[i] = e[i] * e[i];
+  for (int it = 0; it < 200; ++it) {
+    bool any = false;
+    for (int t = 0; t < kw; ++t) {
+      mid_t[t] = 0.5 * (lo_t[t] + hi_t[t]);
+      if (mid_t[t] > lo_t[t] && mid_t[t] < hi_t[t]) any = true;
     }
-    const double th = 0.5 * (a + b);
+    if (!any) break;
+    for (int t = 0; t < kw; ++t) { q_t[t] = d[0] - mid_t[t]; cnt_t[t] = q_t[t] < 0 ? 1 : 0; }
+    for (int i = 1; i < n; ++i) {
+      const double di = d[i], ei2 = e2[i - 1];
+      for (int t = 0; t < kw; ++t) {
+        double q = q_t[t];
+        if (std::fabs(q) < tiny) q = (q < 0 ? -tiny : tiny);
+        q = di - mid_t[t] - ei2 / q;
+        q_t[t] = q;
+        cnt_t[t] += q < 0 ? 1 : 0;
+      }
+    }
+    for (int t = 0; t < kw; ++t) {
+      if (!(mid_t[t] > lo_t[t] && mid_t[t] < hi_t[t])) continue;       // this interval is already down to one ulp
+      if (cnt_t[t] >= n - t) hi_t[t] = mid_t[t]; else lo_t[t] = mid_t[t];   // eigenvalue index n - t (1-based, ascending)
+    }
+  }
+  for (int t = 0; t < k && t < n; ++t) {
+    const double th = 0.5 * (lo_t[t] + hi_t[t]);
     theta[t] = th;
     // inverse iteration; the shift is nudged off the eigenvalue so the LU stays finite
     const double shift = th + nrm * 4.4e-16;
