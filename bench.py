@@ -373,7 +373,8 @@ def main():
         kernels["dvalues"] = cls("dvalues", bytes_each=s1["bytes_dvalues"])
         kernels["kl_loop"] = {"launches": 1, "ms_total": s1["ms_kl_loop"], "swaps": s1["kl_swaps"],
                               "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]),
-                              "state_in_shared_memory": bool(s1.get("kl_local", 0)),
+                              "state": {0: "global memory (cluster kernel)", 1: "tile keys + side bits in shared memory",
+                                        2: "tile keys in shared memory, state bytes in global memory"}.get(int(s1.get("kl_local", 0)), "?"),
                               "bound": "latency (a chain of dependent L2 round trips per swap), not bandwidth"}
         if kernels.get("multidot") and s1.get("gs_fused", 0):
             kernels["multidot"]["note"] = ("fused Gram-Schmidt: ONE cooperative launch per Lanczos step does both passes "

@@ -665,9 +665,16 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
 // The arithmetic (order of the fp32 additions, first-max selection, gain, termination) is unchanged:
 // traces stay byte-identical to cKL.cpp's.
 // ---------------------------------------------------------------------------------------------------
-constexpr int32_t KL_LOCAL_MAX_N = 524288;
+constexpr int32_t KL_LOCAL_MAX_N = 524288;            // tile keys + 2 bits per node in shared memory
+constexpr int32_t KL_LOCAL_GBITS_MAX_N = 2097152;     // tile keys in shared memory, state bytes in global memory
 
 __device__ __forceinline__ unsigned bits_get(const uint32_t *bits, int32_t u) { return (bits[u >> 4] >> ((u & 15) * 2)) & 3u; }
+// GBITS (graphs whose 2 bits per node do not fit beside the tile keys, up to KL_LOCAL_GBITS_MAX_N nodes): the
+// side / locked state is read from the global state bytes instead -- one more dependent load in the row sums
+template <bool GBITS>
+__device__ __forceinline__ unsigned kl_state_get(const uint32_t *bits, const uint8_t *state, int32_t u) {
+  return GBITS ? ((unsigned)__ldcg(state + u) & 3u) : bits_get(bits, u);
+}
 
 // as warp_row_value, sides from the shared-memory bits; (c, ww) = this lane's entry of the row's first 32, already
 // loaded.  The two ordered sums are independent chains -- E only ever grows by the external weights, I by the
@@ -676,9 +683,11 @@ __device__ __forceinline__ unsigned bits_get(const uint32_t *bits, int32_t u) { 
 // same additions in the same order, in max(#E, #I) steps of LDS + FADD instead of 32 steps of shuffle + two
 // FMNMX + two FADD executed by the whole warp (ncu: that replay was ~70% of the loop's 17 K warp instructions
 // per swap, on a kernel whose issue slots are 41% busy).
+template <bool GBITS>
 __device__ __forceinline__ float warp_row_value_local(const int32_t *__restrict__ col, const float *__restrict__ w,
-                                                      const uint32_t *bits, int32_t lo, int32_t hi, int32_t ov_a, int32_t ov_b,
-                                                      int lane, int32_t c, float ww, float *wsm /* 64 floats of this warp */) {
+                                                      const uint32_t *bits, const uint8_t *state, int32_t lo, int32_t hi,
+                                                      int32_t ov_a, int32_t ov_b, int lane, int32_t c, float ww,
+                                                      float *wsm /* 64 floats of this warp */) {
   float acc = 0.0f;                                  // lane 0: E, lane 1: I
   const unsigned lt = (1u << lane) - 1u;
   for (int32_t base = lo; base < hi; base += 32) {
@@ -691,7 +700,7 @@ __device__ __forceinline__ float warp_row_value_local(const int32_t *__restrict_
     if (valid) {
       if (c == ov_a) ext = true;
       else if (c == ov_b) ext = false;
-      else ext = (bits_get(bits, c) & ST_SIDE) != 0u;
+      else ext = (kl_state_get<GBITS>(bits, state, c) & ST_SIDE) != 0u;
     }
     const unsigned P = __ballot_sync(FULL_MASK, valid && ext), N = __ballot_sync(FULL_MASK, valid && !ext);
     if (valid) wsm[ext ? __popc(P & lt) : 32 + __popc(N & lt)] = ww;
@@ -714,23 +723,26 @@ __device__ __forceinline__ unsigned long long kl_key(float v, unsigned side, uin
 }
 
 // best keys of one tile (both sides); one L2 round trip (the D-values, and the ranks unless ASC)
-template <bool ASC>
-__device__ __forceinline__ void tile_scan_local(const uint32_t *bits, const float *val, const uint32_t *__restrict__ rank, int32_t n,
-                                                int32_t tile, int lane, unsigned long long *keys) {
+template <bool ASC, bool GBITS>
+__device__ __forceinline__ void tile_scan_local(const uint32_t *bits, const uint8_t *state, const float *val,
+                                                const uint32_t *__restrict__ rank, int32_t n, int32_t tile, int lane,
+                                                unsigned long long *keys) {
   unsigned long long k0 = 0ull, k1 = 0ull;
   const int32_t base = tile * KL_TILE;
   float vv[KL_TILE / 32];
   uint32_t id[KL_TILE / 32];
+  unsigned sg[KL_TILE / 32];
 #pragma unroll
   for (int r = 0; r < KL_TILE / 32; ++r) {
     const int32_t u = base + r * 32 + lane;
     vv[r] = u < n ? __ldcg(val + u) : 0.0f;
     id[r] = ASC ? (uint32_t)u : (u < n ? __ldg(rank + u) : 0u);
+    sg[r] = (GBITS && u < n) ? ((unsigned)__ldcg(state + u) & 3u) : ST_LOCK;   // same round trip as the D-values
   }
 #pragma unroll
   for (int r = 0; r < KL_TILE / 32; ++r) {
     const int32_t u = base + r * 32 + lane;
-    const unsigned st = u < n ? bits_get(bits, u) : ST_LOCK;
+    const unsigned st = GBITS ? sg[r] : (u < n ? bits_get(bits, u) : ST_LOCK);
     if (!(st & ST_LOCK)) {
       const unsigned long long key = kl_key<ASC>(vv[r], st & ST_SIDE, id[r]);
       if (st & ST_SIDE) k1 = key > k1 ? key : k1;
@@ -767,7 +779,7 @@ __global__ void nb_extent_kernel(const int32_t *__restrict__ rowptr, const int32
   }
 }
 
-template <bool ASC>
+template <bool ASC, bool GBITS>
 __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const KlLocalParams p) {
   extern __shared__ __align__(16) unsigned char kl_sm[];
   unsigned long long *keys = reinterpret_cast<unsigned long long *>(kl_sm);      // 2 * n_tiles
@@ -787,7 +799,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
     sh_done = (p.n0 <= 0 || p.n1 <= 0) ? 1 : 0;
   }
   // side / locked bits of every node: 16 nodes per word
-  const int32_t n_words = (p.n + 15) >> 4;
+  const int32_t n_words = GBITS ? 0 : (p.n + 15) >> 4;
   for (int32_t wd = tid; wd < n_words; wd += KL_LOOP_THREADS) {
     uint32_t v = 0u;
 #pragma unroll
@@ -800,7 +812,8 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
   }
   for (int32_t t = tid; t < p.n_tiles; t += KL_LOOP_THREADS) stamps[t] = 0u;
   __syncthreads();
-  for (int32_t t = warp; t < p.n_tiles; t += KL_LOOP_THREADS / 32) tile_scan_local<ASC>(bits, p.val, p.rank, p.n, t, lane, keys);
+  for (int32_t t = warp; t < p.n_tiles; t += KL_LOOP_THREADS / 32)
+    tile_scan_local<ASC, GBITS>(bits, p.state, p.val, p.rank, p.n, t, lane, keys);
   __syncthreads();
   uint32_t it_local = 0;
 #ifdef EIGKL_KL_CLOCKS
@@ -862,11 +875,13 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
         sh_cut = cut;
         sh_iter = it_local;
         p.t_cut[it_local] = cut; p.t_gain[it_local] = gain; p.t_n1[it_local] = a; p.t_n2[it_local] = b;
-        p.state[a] = (uint8_t)(ST_SIDE | ST_LOCK);                   // swip, cKL.cpp:274-286
-        p.state[b] = (uint8_t)(ST_LOCK);
+        __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));           // swip, cKL.cpp:274-286
+        __stcg(p.state + b, (uint8_t)(ST_LOCK));
         // the workers take a's and b's sides from (a, b) directly, never from these words
-        bits[a >> 4] = (bits[a >> 4] & ~(3u << ((a & 15) * 2))) | ((ST_SIDE | ST_LOCK) << ((a & 15) * 2));
-        bits[b >> 4] = (bits[b >> 4] & ~(3u << ((b & 15) * 2))) | (ST_LOCK << ((b & 15) * 2));
+        if (!GBITS) {
+          bits[a >> 4] = (bits[a >> 4] & ~(3u << ((a & 15) * 2))) | ((ST_SIDE | ST_LOCK) << ((a & 15) * 2));
+          bits[b >> 4] = (bits[b >> 4] & ~(3u << ((b & 15) * 2))) | (ST_LOCK << ((b & 15) * 2));
+        }
         // a and b held the best keys of their tiles: those tiles are rescanned
         if (atomicExch(stamps + a / KL_TILE, stamp) != stamp) list[atomicAdd(&sh_nlist, 1)] = a / KL_TILE;
         if (atomicExch(stamps + b / KL_TILE, stamp) != stamp) list[atomicAdd(&sh_nlist, 1)] = b / KL_TILE;
@@ -910,10 +925,10 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
             if (j0 + u < cnt) {                                    // warp-uniform
               const int32_t v = __shfl_sync(FULL_MASK, my_v, j0 + u);
               const uint32_t vid = __shfl_sync(FULL_MASK, my_id, j0 + u);
-              const float nv = warp_row_value_local(p.col, p.w, bits, lo[u], hi[u], a, b, lane, c[u], ww[u], sh_wsm[warp]);
+              const float nv = warp_row_value_local<GBITS>(p.col, p.w, bits, p.state, lo[u], hi[u], a, b, lane, c[u], ww[u], sh_wsm[warp]);
               if (lane == 0) {
                 __stcg(p.val + v, nv);
-                const unsigned st = bits_get(bits, v);
+                const unsigned st = kl_state_get<GBITS>(bits, p.state, v);
                 if (!(st & ST_LOCK) && v != a && v != b) {
                   // the tile's key: raised in place, unless v itself held it (then the tile is rescanned)
                   const int32_t tile = v / KL_TILE;
@@ -937,7 +952,8 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
     // ---- S4: rescan the few tiles whose best node was touched or locked, one per warp ----
     {
       const int nl = sh_nlist;
-      for (int q = warp; q < nl; q += KL_LOOP_THREADS / 32) tile_scan_local<ASC>(bits, p.val, p.rank, p.n, list[q], lane, keys);
+      for (int q = warp; q < nl; q += KL_LOOP_THREADS / 32)
+        tile_scan_local<ASC, GBITS>(bits, p.state, p.val, p.rank, p.n, list[q], lane, keys);
     }
     KL_PHASE(4);
     __syncthreads();
@@ -971,7 +987,8 @@ void kl_run(eigkl_handle *h) {
   int32_t own_lo = 0, own_hi = n, own_pad = 0;
   if (R > 1) row_partition(n, R, h->opts.rank, &own_lo, &own_hi, &own_pad);
   // state in shared memory (one CTA) whenever it fits, unless a cluster size was asked for explicitly
-  const bool local = R == 1 && h->kl_local && h->opts.kl_cluster <= 0 && n <= KL_LOCAL_MAX_N;
+  const bool local = R == 1 && h->kl_local && h->opts.kl_cluster <= 0 && n <= KL_LOCAL_GBITS_MAX_N;
+  const bool gbits = local && (n > KL_LOCAL_MAX_N || getenv("EIGKL_KL_GBITS") != nullptr);
   if (!local) {
     tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, own_lo, own_hi, n_tiles, k.tile_key.p, k.tile_stamp.p);
     h->launches++;
@@ -1031,16 +1048,24 @@ void kl_run(eigkl_handle *h) {
     q.state = k.state.p; q.rank = k.rank.p; q.val = k.val.p; q.order0 = k.order0.p; q.order1 = k.order1.p;
     q.t_cut = k.t_cut.p; q.t_gain = k.t_gain.p; q.t_n1 = k.t_n1.p; q.t_n2 = k.t_n2.p;
     q.ctrl = k.ctrl.p; q.cut0 = cut0; q.term_limit = p.term_limit; q.n0 = k.n0; q.n1 = k.n1;
-    const size_t smem = (size_t)n_tiles * (16 + 4 + 4) + (size_t)((n + 15) / 16) * 4 + 16;
+    const size_t smem = (size_t)n_tiles * (16 + 4 + 4) + (gbits ? 0 : (size_t)((n + 15) / 16) * 4) + 16;
     if (!h->attr_kl_local) {
-      const size_t max_smem = (size_t)(KL_LOCAL_MAX_N / KL_TILE) * 24 + (size_t)(KL_LOCAL_MAX_N / 16) * 4 + 16;
-      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      const size_t max_smem = std::max((size_t)(KL_LOCAL_MAX_N / KL_TILE) * 24 + (size_t)(KL_LOCAL_MAX_N / 16) * 4,
+                                       (size_t)(KL_LOCAL_GBITS_MAX_N / KL_TILE) * 24) + 16;
+      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+      EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_local_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
       h->attr_kl_local = true;
     }
     nc = 1;
-    if (k.ascending) kl_loop_local_kernel<true><<<1, KL_LOOP_THREADS, smem, st>>>(q);
-    else kl_loop_local_kernel<false><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+    if (k.ascending) {
+      if (gbits) kl_loop_local_kernel<true, true><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+      else kl_loop_local_kernel<true, false><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+    } else {
+      if (gbits) kl_loop_local_kernel<false, true><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+      else kl_loop_local_kernel<false, false><<<1, KL_LOOP_THREADS, smem, st>>>(q);
+    }
     EIGKL_CUDA(cudaGetLastError());
     h->launches++;
   } else if (R == 1) {
@@ -1088,7 +1113,7 @@ void kl_run(eigkl_handle *h) {
   }
   h->stats.kl_cluster = nc;
   h->stats.kl_threads = nc * KL_LOOP_THREADS;
-  h->stats.kl_local = local ? 1 : 0;
+  h->stats.kl_local = local ? (gbits ? 2 : 1) : 0;
 }
 
 }  // namespace eigkl

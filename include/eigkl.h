@@ -93,7 +93,8 @@ typedef struct {
    * n_multidot / ms_multidot; n_update stays 0), 0 when they are separate multidot/update launches */
   int32_t  gs_fused;
   int32_t  gs_cache_cols;        /* basis columns the fused kernel keeps in shared memory            */
-  int32_t  kl_local;             /* 1: the swap loop ran as one CTA with tile keys and side bits in shared memory */
+  int32_t  kl_local;             /* swap loop as one CTA: 1 = tile keys and side bits in shared memory, 2 = tile keys
+                                  * in shared memory and state bytes in global memory; 0 = global-memory cluster kernel */
   int32_t  reserved0;
 } eigkl_stats;
 

@@ -119,6 +119,30 @@ def test_kl_trace_byte_exact_vs_reference(c, handles, workdir, tmp_path):
     assert int(side.sum()) == h.n_nodes - (h.n_nodes + 1) // 2 or int(side.sum()) > 0
 
 
+@pytest.mark.parametrize("c", CIRCUITS)
+@pytest.mark.parametrize("variant", ["shared_bits", "global_bits", "global_state"])
+def test_kl_loop_variants_byte_exact(c, variant, circuits, workdir, tmp_path, monkeypatch):
+    """The three single-GPU swap loops -- tile keys + side bits in shared memory (default up to 524 288 nodes), tile
+    keys in shared memory with the state bytes in global memory (up to 2 M nodes), everything in global memory (the
+    cluster kernel) -- all reproduce the reference's one-core trace byte for byte."""
+    if variant == "global_bits":
+        monkeypatch.setenv("EIGKL_KL_GBITS", "1")
+    if variant == "global_state":
+        monkeypatch.setenv("EIGKL_KL_LOCAL", "0")
+    with api.Handle() as h:
+        h.load_hgr(circuits[c])
+        h.assemble_kl_graph()
+        h.load_eig(datasets.golden_eig_path(workdir, c))
+        tr = h.kl_run()
+        assert h.stats()["kl_local"] == {"shared_bits": 1, "global_bits": 2, "global_state": 0}[variant]
+    out = str(tmp_path / "trace.txt")
+    api.write_trace(out, tr)
+    raw = open(out, "rb").read()
+    assert raw == open(os.path.join(GOLDEN, c + ".kl_trace_1core.txt"), "rb").read()
+    n1, n2 = golden_swaps(c)
+    assert np.array_equal(tr["node1"][1:], n1) and np.array_equal(tr["node2"][1:], n2)
+
+
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8, 16])
 def test_kl_cluster_sizes_agree(cluster, oracle, circuits, workdir):
     c = "industry2"

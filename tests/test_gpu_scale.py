@@ -116,6 +116,7 @@ def test_two_million_node_synthetic_properties(tmp_path):
         assert abs(int(side0.sum()) - h.n_nodes // 2) <= h.n_nodes // 2     # any split is legal for a null vector
         h.assemble_kl_graph()
         tr = h.kl_run()
+        assert h.stats()["kl_local"] == 2                       # one CTA: tile keys in shared memory, state bytes in global memory
         assert tr["swaps"] > 1000
         assert tr["cut"].min() <= tr["cut"][0]
         _kl_invariants(h, tr, side0)
