@@ -248,6 +248,8 @@ update_kernel(const double *__restrict__ V, size_t ld, int ncols, double *__rest
 // ---------------------------------------------------------------------------------------------------
 constexpr int GS_THREADS = 1024;
 constexpr int GS_MAX_ROWS = 2048;
+constexpr int GS_B = 8;                // loads in flight per lane when a basis column is read from global memory
+                                       // (16 spills at the kernel's 64-register cap and measured no faster)
 struct GsArgs {
   const double *V;
   size_t ld;
@@ -312,12 +314,12 @@ __device__ __forceinline__ void gs_dots(const GsArgs &A, const double *ws, doubl
     double *vs = Vs + (size_t)c * R;
     const bool keep = FILL && c < A.cache_cols;
     double acc0 = 0.0, acc1 = 0.0;
-    for (int r = lane; r < R; r += 256) {
-      double v[8];
+    for (int r = lane; r < R; r += 32 * GS_B) {
+      double v[GS_B];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) v[u] = (r + 32 * u < rows) ? col[r + 32 * u] : 0.0;
+      for (int u = 0; u < GS_B; ++u) v[u] = (r + 32 * u < rows) ? col[r + 32 * u] : 0.0;
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < GS_B; ++u) {
         const int rr = r + 32 * u;
         if (rr < R) {
           if (keep) vs[rr] = v[u];
