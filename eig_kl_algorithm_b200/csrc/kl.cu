@@ -1105,7 +1105,7 @@ void kl_run(eigkl_handle *h) {
   EIGKL_REQUIRE(ctrl[1] == 1, EIGKL_E_CUDA, "KL kernel did not complete");
   k.swaps = ctrl[0];
   h->stats.kl_swaps = k.swaps;
-  if (getenv("EIGKL_KL_PHASES") && R == 1 && k.swaps > 0) {
+  if (getenv("EIGKL_KL_PHASES") && R == 1 && !local && k.swaps > 0) {   // the global-memory loop carries the clocks
     static const char *nm[6] = {"S1 reduce", "decode", "S3 own rows", "S3 barrier wait", "S4 own tiles", "S4 barrier wait"};
     fprintf(stderr, "[eigkl] KL phases, cycles per swap (thread 0):");
     for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f;", nm[i], (double)ctrl[8 + i] / (double)k.swaps);
