@@ -23,7 +23,7 @@ ERRORS = {0: "OK", -1: "E_ARG", -2: "E_IO", -3: "E_FORMAT", -4: "E_CUDA", -5: "E
 # every symbol include/eigkl.h declares (checked by tests/test_cabi.py against the header itself)
 SYMBOLS = [
     "eigkl_abi_version", "eigkl_nccl_unique_id", "eigkl_create", "eigkl_destroy", "eigkl_last_error",
-    "eigkl_get_stats", "eigkl_synchronize", "eigkl_load_hgr", "eigkl_set_pins", "eigkl_get_sizes",
+    "eigkl_get_stats", "eigkl_synchronize", "eigkl_set_profile", "eigkl_load_hgr", "eigkl_set_pins", "eigkl_get_sizes",
     "eigkl_invalidate", "eigkl_get_stream", "eigkl_row_partition",
     "eigkl_assemble_laplacian", "eigkl_fiedler", "eigkl_partition_from_fiedler", "eigkl_write_eig",
     "eigkl_assemble_kl_graph", "eigkl_set_partition", "eigkl_set_partition_ordered", "eigkl_load_eig",
@@ -65,7 +65,9 @@ class Stats(C.Structure):
                 ("bytes_multidot_total", C.c_double), ("bytes_update_total", C.c_double),
                 ("spmv_per_launch", C.c_int32), ("resident_k", C.c_int32),
                 ("gs_fused", C.c_int32), ("gs_cache_cols", C.c_int32),
-                ("kl_local", C.c_int32), ("reserved0", C.c_int32)]
+                ("kl_local", C.c_int32), ("reserved0", C.c_int32),
+                ("dist_ranks", C.c_int32), ("dist_rows", C.c_int32), ("dist_halo", C.c_int64), ("dist_exports", C.c_int64),
+                ("ms_comm", C.c_double), ("ms_push", C.c_double), ("n_comm", C.c_int64), ("n_push", C.c_int64)]
 
     def as_dict(self):
         d = {}
@@ -103,6 +105,7 @@ def load_library(path=LIB_PATH):
     L.eigkl_last_error.restype = C.c_char_p
     L.eigkl_get_stats.argtypes = [H, P(Stats)]
     L.eigkl_synchronize.argtypes = [H]
+    L.eigkl_set_profile.argtypes = [H, C.c_int]
     L.eigkl_load_hgr.argtypes = [H, C.c_char_p]
     L.eigkl_set_pins.argtypes = [H, C.c_int32, C.c_int32, P(C.c_int64), P(C.c_int32)]
     L.eigkl_get_sizes.argtypes = [H, P(C.c_int32), P(C.c_int32), P(C.c_int64)]
@@ -252,23 +255,20 @@ class Handle:
         side = np.ascontiguousarray(side, dtype=np.uint8)
         assert len(side) == self.n_nodes
         self._check(self.lib.eigkl_set_partition(self._h, _ptr(side, C.c_uint8)))
-        self._cap = int(min((side == 0).sum(), (side == 1).sum())) + 1
 
     def set_partition_ordered(self, order0, order1):
         o0 = np.ascontiguousarray(order0, dtype=np.int32)
         o1 = np.ascontiguousarray(order1, dtype=np.int32)
         self._check(self.lib.eigkl_set_partition_ordered(self._h, _ptr(o0, C.c_int32), len(o0), _ptr(o1, C.c_int32), len(o1)))
-        self._cap = min(len(o0), len(o1)) + 1
 
     def load_eig(self, path):
         self._check(self.lib.eigkl_load_eig(self._h, os.fsencode(path)))
-        self._cap = self.n_nodes // 2 + 2
 
     def kl_run(self, want_trace=True):
         if not want_trace:
             self._check(self.lib.eigkl_kl_run(self._h, None))
             return None
-        cap = getattr(self, "_cap", self.n_nodes // 2 + 2)
+        cap = self.n_nodes // 2 + 2          # >= min(|left|, |right|) + 1 whatever the partition is
         cut = np.zeros(cap, np.float32)
         gain = np.zeros(cap, np.float32)
         n1 = np.zeros(cap, np.int32)
@@ -339,6 +339,9 @@ class Handle:
         ms = C.c_double()
         self._check(self.lib.eigkl_time_kernel(self._h, {"spmv": 0, "dvalues": 1}[what], iters, int(flush_l2), C.byref(ms)))
         return ms.value
+
+    def set_profile(self, on):
+        self._check(self.lib.eigkl_set_profile(self._h, int(bool(on))))
 
     def synchronize(self):
         self._check(self.lib.eigkl_synchronize(self._h))

@@ -28,7 +28,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
                      "-ccbin", HOST_CXX, "-I" + os.path.join(ROOT, "include"), "-I" + CSRC,
                      "--expt-relaxed-constexpr", "-Xptxas", "-v"]
-SOURCES = ["scan_sort.cu", "assemble.cu", "spmv.cu", "lanczos.cu", "kl.cu", "dense_eig.cpp", "hgr_io.cpp",
+SOURCES = ["scan_sort.cu", "assemble.cu", "spmv.cu", "lanczos.cu", "dist.cu", "kl.cu", "dense_eig.cpp", "hgr_io.cpp",
            "cabi.cpp", "comm.cpp"]
 HEADERS = ["internal.h", "device_utils.cuh", "stl_order.h", os.path.join(ROOT, "include", "eigkl.h")]
 CLIS = ["cEIG", "cKL", "gKL"]

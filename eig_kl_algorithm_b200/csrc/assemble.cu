@@ -24,11 +24,14 @@ constexpr int TPB = 256;
 static inline unsigned grid_for(int64_t n, int tpb = TPB) { return (unsigned)((n + tpb - 1) / tpb > 0 ? (n + tpb - 1) / tpb : 1); }
 
 // ------------------------------------------------------------------------------------------------
+// also validates the offsets: a non-monotonic net_off would give negative net sizes, and k(k-1)/2 is positive for
+// negative k too, so the pair expansion would index pins[] out of bounds (err bit 4 -> EIGKL_E_FORMAT)
 __global__ void net_pair_count_kernel(const int64_t *__restrict__ net_off, int32_t n_nets,
-                                      int64_t *__restrict__ cnt) {
+                                      int64_t *__restrict__ cnt, int *__restrict__ err) {
   int32_t e = blockIdx.x * blockDim.x + threadIdx.x;
   if (e < n_nets) {
     int64_t k = net_off[e + 1] - net_off[e];
+    if (k < 0) { atomicOr(err, 4); k = 0; }
     cnt[e] = k * (k - 1) / 2;
   }
 }
@@ -155,13 +158,14 @@ void upload_pins(eigkl_handle *h, int32_t n_nodes, int32_t n_nets, const int64_t
   auto &err = h->scr.err; err.alloc(1);
   EIGKL_CUDA(cudaMemsetAsync(err.p, 0, sizeof(int), h->stream));
   if (n_pins) { validate_pins_kernel<<<grid_for(n_pins), TPB, 0, h->stream>>>(g.pins.p, n_pins, n_nodes, err.p); h->launches++; }
-  if (n_nets) { net_pair_count_kernel<<<grid_for(n_nets), TPB, 0, h->stream>>>(g.net_off.p, n_nets, g.pair_off.p); h->launches++; }
+  if (n_nets) { net_pair_count_kernel<<<grid_for(n_nets), TPB, 0, h->stream>>>(g.net_off.p, n_nets, g.pair_off.p, err.p); h->launches++; }
   exclusive_scan_i64(h, g.pair_off.p, g.pair_off.p, n_nets);
   int herr = 0;
   int64_t P = 0;
   EIGKL_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaMemcpyAsync(&P, g.pair_off.p + n_nets, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  EIGKL_REQUIRE((herr & 4) == 0, EIGKL_E_FORMAT, "net_off is not non-decreasing");
   EIGKL_REQUIRE(herr == 0, EIGKL_E_FORMAT, "pin id out of range [1, nodes]");
   EIGKL_REQUIRE(P < (int64_t)2147483647, EIGKL_E_ARG, "more than 2^31-1 clique pairs");
   g.n_pairs = P;
@@ -430,18 +434,14 @@ void assemble_laplacian(eigkl_handle *h) {
   diag_decode_kernel<<<1, 32, 0, h->stream>>>(L.diag_minmax.p, reinterpret_cast<double *>(L.diag_minmax.p + 2));
   double dmm[2] = {0, 0};
   EIGKL_CUDA(cudaMemcpyAsync(dmm, L.diag_minmax.p + 2, sizeof(dmm), cudaMemcpyDeviceToHost, h->stream));
-  // this rank's row slice (the matrix itself is assembled in full on every rank: ~1 ms, and it keeps
-  // the assembly free of collectives; SpMV and every vector are row-partitioned)
-  int32_t n_pad = 0;
-  row_partition(n, h->opts.nranks, h->opts.rank, &L.row_lo, &L.row_hi, &n_pad);
-  int32_t rp[2] = {0, 0};
-  EIGKL_CUDA(cudaMemcpyAsync(&rp[0], L.rowptr.p + L.row_lo, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
-  EIGKL_CUDA(cudaMemcpyAsync(&rp[1], L.rowptr.p + L.row_hi, sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
   cheb_resident_plan(h);     // resident polynomial filter (spmv.cu): plan enqueued, checked after the sync
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   L.diag_min = dmm[0]; L.diag_max = dmm[1];
   cheb_resident_plan_finish(h);
-  const int64_t nnz_local = (int64_t)rp[1] - rp[0];
+  // The matrix itself is assembled in full on every rank (~1 ms, and it keeps the assembly free of collectives).
+  // With several ranks: a matrix that fits one chip is SOLVED on every rank as well; a larger one is cut into
+  // nnz-balanced row ranges, and SpMV and every Lanczos vector are row-partitioned (dist.cu).
+  const int64_t nnz_local = dist_decide(h);
   // which SpMV kernel runs this matrix: the flat kernel (shared-memory staged row blocks, one round of loads
   // per block; blocks that hold a row too long for the staging buffer fall back to warp-per-row inside it).
   // Measured warm, flat vs sub-warp: ibm01 5.1 vs 7.3 us, ibm10 10.3 vs 14.4, industry2 10.4 vs 12.4,
@@ -457,10 +457,14 @@ void assemble_laplacian(eigkl_handle *h) {
   h->launches++;
   h->launches += 3;
   EIGKL_CUDA(cudaGetLastError());
+  h->stats.dist_ranks = 1; h->stats.dist_rows = n; h->stats.dist_halo = 0; h->stats.dist_exports = 0;
+  dist_plan(h);              // halo / export lists of this rank's rows (row-partitioned mode only)
   L.valid = true;
   h->stats.nnz_laplacian = L.nnz;
-  // algorithmic bytes of one SpMV: nnz*(8 val + 4 col) + n*(4 rowptr + 8 x + 8 y)   
-  h->stats.bytes_spmv = (double)L.nnz * 12.0 + (double)n * 20.0;
+  // algorithmic bytes of one SpMV: nnz*(8 val + 4 col) + n*(4 rowptr + 8 x + 8 y)   (SURVEY.md 8d); row-partitioned:
+  // this rank's share (its rows' entries, its rows of x / y) -- the halo values it receives are counted as x reads
+  h->stats.bytes_spmv = h->dist.valid ? (double)h->dist.nnz_l * 12.0 + (double)h->dist.nl * 20.0 + (double)h->stats.dist_halo * 8.0
+                                      : (double)L.nnz * 12.0 + (double)n * 20.0;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -79,6 +79,8 @@ static void sync_profile_into_stats(eigkl_handle *h) {
   s.ms_update = p.ms[KC_UPDATE]; s.n_update = p.cnt[KC_UPDATE];
   s.ms_restart = p.ms[KC_RESTART]; s.n_restart = p.cnt[KC_RESTART];
   s.ms_dvalues = p.ms[KC_DVALUES]; s.n_dvalues = p.cnt[KC_DVALUES];
+  s.ms_comm = p.ms[KC_COMM]; s.n_comm = p.cnt[KC_COMM];
+  s.ms_push = p.ms[KC_PUSH]; s.n_push = p.cnt[KC_PUSH];
   s.gpu_launches = h->launches;
 }
 
@@ -132,8 +134,11 @@ int eigkl_create(eigkl_handle **out, const eigkl_opts *opts) {
     if (const char *m = getenv("EIGKL_SPMV_PDL")) h->spmv_pdl = atoi(m);
     if (const char *m = getenv("EIGKL_SPMV_RESIDENT")) h->spmv_resident = atoi(m);
     if (const char *m = getenv("EIGKL_GS_FUSED")) h->gs_fused = atoi(m);
-    if (const char *m = getenv("EIGKL_COOP")) h->coop_launch = atoi(m);
     if (const char *m = getenv("EIGKL_KL_LOCAL")) h->kl_local = atoi(m);
+    if (const char *m = getenv("EIGKL_DIST")) {       // rows | replicate | auto
+      h->dist_mode = (strcmp(m, "rows") == 0 || strcmp(m, "1") == 0) ? 1 : (strcmp(m, "replicate") == 0 || strcmp(m, "2") == 0) ? 2 : 0;
+    }
+    if (const char *m = getenv("EIGKL_KL_DIST")) h->kl_dist = atoi(m);
     h->stats.struct_size = sizeof(eigkl_stats);
     if (h->opts.nranks > 1) comm_init(h);
     *out = h;
@@ -141,12 +146,12 @@ int eigkl_create(eigkl_handle **out, const eigkl_opts *opts) {
   } catch (const eigkl::Error &e) {
     std::lock_guard<std::mutex> lk(g_create_mutex);
     g_create_error = e.what();
-    delete h;
+    eigkl_destroy(h);            // releases whatever was already created (stream, timer events, communicator)
     return e.code;
   } catch (...) {
     std::lock_guard<std::mutex> lk(g_create_mutex);
     g_create_error = "eigkl_create: unknown error";
-    delete h;
+    eigkl_destroy(h);
     return EIGKL_E_NOMEM;
   }
 }
@@ -155,7 +160,8 @@ void eigkl_destroy(eigkl_handle *h) {
   if (!h) return;
   cudaSetDevice(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  comm_destroy(h);
+  peer_arena_destroy(h);
+  try { comm_destroy(h); } catch (...) {}
   if (h->l2_flush) cudaFree(h->l2_flush);
   h->timer.destroy();
   cudaStream_t s = h->stream;
@@ -175,6 +181,16 @@ int eigkl_get_stats(const eigkl_handle *hc, eigkl_stats *out) {
     sync_profile_into_stats(h);
     *out = h->stats;
     out->struct_size = sizeof(eigkl_stats);
+  });
+}
+
+int eigkl_set_profile(eigkl_handle *h, int on) {
+  return guarded(h, [&] {
+    EIGKL_CUDA(cudaSetDevice(h->device));
+    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+    h->prof.reset();
+    h->prof.on = on != 0;
+    h->stats.bytes_multidot_total = h->stats.bytes_update_total = 0.0;
   });
 }
 
@@ -330,14 +346,21 @@ int eigkl_load_eig(eigkl_handle *h, const char *path) {
     EIGKL_REQUIRE(h->hg.loaded, EIGKL_E_ARG, "eigkl_load_eig: load the hypergraph first");
     EIGKL_CUDA(cudaSetDevice(h->device));
     std::vector<uint8_t> side;
-    read_eig_file(path, h->hg.n_nodes, side);
-    kl_set_partition(h, side.data(), nullptr, 0, nullptr, 0, true);
+    std::vector<int32_t> o0, o1;
+    bool asc = true;
+    read_eig_file(path, h->hg.n_nodes, side, o0, o1, asc);
+    if (asc) kl_set_partition(h, side.data(), nullptr, 0, nullptr, 0, true);
+    else kl_set_partition(h, nullptr, o0.data(), (int64_t)o0.size(), o1.data(), (int64_t)o1.size(), false);   // cKL.cpp:166-173
   });
 }
 
 int eigkl_kl_run(eigkl_handle *h, eigkl_trace *trace) {
   return guarded(h, [&] {
     EIGKL_CUDA(cudaSetDevice(h->device));
+    // checked BEFORE the pass runs: a short trace must not cost a whole pass
+    if (trace && h->kl.have_partition)
+      EIGKL_REQUIRE(trace->capacity >= std::min(h->kl.n0, h->kl.n1) + 1, EIGKL_E_ARG,
+                    "eigkl_trace.capacity too small (need min(|left|,|right|)+1)");
     kl_run(h);
     if (trace) {
       auto &k = h->kl;
@@ -383,10 +406,9 @@ int eigkl_spmv(eigkl_handle *h, const double *x, double *y) {
     EIGKL_REQUIRE(x && y && h->L.valid, EIGKL_E_ARG, "eigkl_spmv: Laplacian not assembled");
     EIGKL_CUDA(cudaSetDevice(h->device));
     const size_t n = (size_t)h->L.n;
-    int32_t lo, hi, n_pad;
-    row_partition(h->L.n, h->opts.nranks, h->opts.rank, &lo, &hi, &n_pad);
-    const size_t full = (size_t)n_pad * (size_t)h->opts.nranks;
-    DBuf<double> dx, dy, dg; dx.alloc(n); dy.alloc((size_t)n_pad); dg.alloc(full);
+    const bool dist = h->dist.valid;
+    const int32_t n_pad = dist ? h->dist.n_pad : (int32_t)(ceil_div(h->L.n, 32) * 32);
+    DBuf<double> dx, dy, dg; dx.alloc(n); dy.alloc((size_t)n_pad); dg.alloc(n);
     std::vector<int32_t> perm(n);
     EIGKL_CUDA(cudaMemcpyAsync(perm.data(), h->order.perm.p, n * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
     EIGKL_CUDA(cudaStreamSynchronize(h->stream));
@@ -394,9 +416,18 @@ int eigkl_spmv(eigkl_handle *h, const double *x, double *y) {
     for (size_t i = 0; i < n; ++i) xp[i] = x[perm[i]];                // file ids -> the matrix's node order
     EIGKL_CUDA(cudaMemcpyAsync(dx.p, xp.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     EIGKL_CUDA(cudaMemsetAsync(dy.p, 0, (size_t)n_pad * sizeof(double), h->stream));
-    spmv_launch(h, dx.p, dy.p, nullptr, nullptr);             // this rank's rows
     const double *src = dy.p;
-    if (h->opts.nranks > 1) { comm_allgather_f64(h, dy.p, dg.p, (size_t)n_pad); src = dg.p; }
+    if (dist) {
+      // row-partitioned: this rank's rows of x into the stage buffer, halo pushed by the peers, rows of y gathered
+      dist_stage_load(h, dx.p + h->L.row_lo);
+      SpmvDist d{dist_push(h, 3), 0u, 0};
+      spmv_launch_ex(h, dist_buf(h, 3), dist_own(h, 3), nullptr, dy.p, nullptr, nullptr, 1.0, 0.0, 0.0, &d);
+      dist_gather_full(h, dy.p, dg.p);
+      dist_check(h);
+      src = dg.p;
+    } else {
+      spmv_launch(h, dx.p, dy.p, nullptr, nullptr);
+    }
     EIGKL_CUDA(cudaMemcpyAsync(yp.data(), src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     EIGKL_CUDA(cudaStreamSynchronize(h->stream));
     for (size_t i = 0; i < n; ++i) y[perm[i]] = yp[i];

@@ -89,6 +89,12 @@ void comm_allgather_f64(eigkl_handle *h, const double *send, double *recv, size_
 void comm_broadcast_bytes(eigkl_handle *h, void *buf, size_t bytes, int root) {
   EIGKL_NCCL(nccl().Broadcast(buf, buf, bytes, ncclChar, root, (ncclComm_t)h->nccl_comm, h->stream));
 }
+void comm_allgather_bytes(eigkl_handle *h, const void *send, void *recv, size_t bytes_per_rank) {
+  EIGKL_NCCL(nccl().AllGather(send, recv, bytes_per_rank, ncclChar, (ncclComm_t)h->nccl_comm, h->stream));
+}
+void comm_allreduce_min_i32(eigkl_handle *h, int32_t *buf, size_t count) {
+  EIGKL_NCCL(nccl().AllReduce(buf, buf, count, ncclInt32, ncclMin, (ncclComm_t)h->nccl_comm, h->stream));
+}
 #else
 void comm_unique_id(void *) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
 void comm_init(eigkl_handle *) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
@@ -97,6 +103,8 @@ void comm_allreduce_sum_f64(eigkl_handle *, double *, size_t) { throw Error(EIGK
 void comm_allreduce_max_u64(eigkl_handle *, unsigned long long *, size_t) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
 void comm_allgather_f64(eigkl_handle *, const double *, double *, size_t) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
 void comm_broadcast_bytes(eigkl_handle *, void *, size_t, int) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
+void comm_allgather_bytes(eigkl_handle *, const void *, void *, size_t) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
+void comm_allreduce_min_i32(eigkl_handle *, int32_t *, size_t) { throw Error(EIGKL_E_NCCL, "libeigkl was built without NCCL"); }
 #endif
 
 }  // namespace eigkl

@@ -116,7 +116,7 @@ struct KernelProfiler {
   void reset();
   ~KernelProfiler();
 };
-enum { KC_SPMV = 0, KC_MULTIDOT = 1, KC_UPDATE = 2, KC_RESTART = 3, KC_DVALUES = 4 };
+enum { KC_SPMV = 0, KC_MULTIDOT = 1, KC_UPDATE = 2, KC_RESTART = 3, KC_DVALUES = 4, KC_COMM = 5, KC_PUSH = 6 };
 
 // ---------------------------------------------------------------------------------------------------
 // device-resident problem state
@@ -184,6 +184,51 @@ struct LaplacianCsr {          // fp64, symmetric, rows ascending by column, dia
   bool valid = false;
 };
 
+// ---------------------------------------------------------------------------------------------------
+// Row-partitioned Lanczos across ranks (nranks > 1 and the matrix does not fit the chip).
+// Rank r owns rows [cuts[r], cuts[r+1]) -- nnz-balanced cuts on multiples of 32 -- of L and of every Lanczos
+// vector.  A rank's SpMV input lives in ONE buffer of R slots x n_pad doubles: slot `me` holds its own rows,
+// slot p != me holds, packed in ascending column order, the HALO it needs from rank p (the distinct columns in
+// p's range that its rows reference).  L is symmetric, so "rows of p that q references" can be computed by p
+// from its own rows alone: no plan exchange between ranks.  Producers push their export rows straight into the
+// consumers' slots over NVLink (peer-mapped memory) from the SpMV epilogue, then raise a flag (dist.cu, spmv.cu).
+// ---------------------------------------------------------------------------------------------------
+constexpr int EIGKL_MAX_RANKS = 16;
+struct DistPlan {
+  int R = 1, me = 0;
+  int32_t cuts[EIGKL_MAX_RANKS + 1] = {0};
+  int32_t n_pad = 0;             // slot size: the largest row count of a rank, rounded up to 32
+  int32_t nl = 0;                // rows of this rank
+  int32_t e_lo = 0;              // rowptr[cuts[me]]: first entry of this rank's rows
+  int64_t nnz_l = 0;
+  DBuf<int32_t> col_c;           // nnz_l: index into the x buffer (slot * n_pad + position) of every local entry
+  DBuf<uint32_t> bm_halo;        // one bit per column: referenced by my rows and owned by another rank
+  DBuf<int32_t> pre_halo;        // exclusive popcount prefix over bm_halo's words
+  DBuf<uint32_t> bm_exp;         // R bitmaps over my rows: row is referenced by rank q
+  DBuf<int32_t> pre_exp;
+  DBuf<int32_t> exp_ids;         // R x n_pad: my rows (local offsets) that rank q needs, ascending
+  DBuf<int32_t> exp_cnt;         // R
+  DBuf<int32_t> blk_exp;         // (n_blocks + 1) x R: export rows of rank q below the row block's first row
+  int32_t exp_cnt_host[EIGKL_MAX_RANKS] = {0};
+  int32_t halo_cnt_host[EIGKL_MAX_RANKS] = {0};
+  bool valid = false;
+};
+
+// Peer-mapped exchange arena (cudaIpc): [flags | w0 | w1 | w2 | stage], each vector R x n_pad doubles.  Grow-only;
+// the mappings are re-opened only when the arena grows.
+struct PeerArena {
+  void *base = nullptr;
+  size_t bytes = 0;
+  size_t vec_bytes = 0;          // bytes of one vector buffer in the current layout
+  void *peer[EIGKL_MAX_RANKS] = {nullptr};   // peer[q]: rank q's arena in this process' address space
+  DBuf<unsigned long long> dev_ptrs;         // the same table on the device
+  DBuf<unsigned int> ticket;     // last-CTA tickets of the push kernels
+  DBuf<int> err;                 // [0] != 0: a flag wait timed out
+  uint32_t seq = 0;              // halo productions issued so far (identical on every rank)
+  int state = 0;                 // 0 untried, 1 usable, -1 peer mapping unavailable (every rank then solves replicated)
+};
+constexpr size_t PEER_FLAGS_BYTES = 4096;
+
 struct KlCsr {                 // fp32, symmetric, rows in reference traversal order
   int32_t n = 0;
   int64_t nnz = 0;
@@ -206,6 +251,7 @@ struct KlState {
   int64_t n0 = 0, n1 = 0;
   bool ascending = true;       // remain orders are ascending ids (the -EIG branch)
   bool have_partition = false;
+  bool consumed = false;       // a pass ran over this partition: state[] carries lock bits and swapped sides, orders are stale
   // trace on device
   DBuf<float> t_cut, t_gain;
   DBuf<int32_t> t_n1, t_n2;
@@ -258,6 +304,10 @@ struct eigkl_handle {
   eigkl::UniqueEdges ueL;      // edges in the relabelled ids (Laplacian)
   eigkl::NodeOrder order;
   eigkl::LaplacianCsr L;
+  eigkl::DistPlan dist;
+  eigkl::PeerArena arena;
+  int dist_mode = 0;           // EIGKL_DIST: 0 auto (replicate when the matrix fits the chip), 1 always row-partition, 2 always replicate
+  int kl_dist = 0;             // EIGKL_KL_DIST=1: KL partitioned by node range with one NCCL arg-max per swap (tested option)
   eigkl::KlCsr A;
   eigkl::KlState kl;
   eigkl::EigState eig;
@@ -269,7 +319,6 @@ struct eigkl_handle {
   bool attr_kl_local = false, attr_gs = false, attr_resident = false;
   int coop_ok = -1;            // -1 unknown, 0/1: cudaDevAttrCooperativeLaunch
   int kl_local = 1;            // EIGKL_KL_LOCAL=0: never run the swap loop with its state in shared memory
-  int coop_launch = 1;         // EIGKL_COOP=0: launch the grid-synchronising kernels without the cooperative attribute (tuning aid)
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
   // scratch of the sort / scan primitives
@@ -314,8 +363,24 @@ void spmv_resident_print_phases();
 void cheb_resident_plan(eigkl_handle *h);          // enqueue (no sync)
 void cheb_resident_plan_finish(eigkl_handle *h);   // after the stream has been synchronised
 void resident_row_blocks(eigkl_handle *h, int64_t chunk);   // assemble.cu
+struct SpmvDist {              // row-partitioned SpMV: which halo production the input carries / the output becomes
+  uint32_t wait_seq;           // the input buffer's halo slots are complete once every peer's flag reaches this
+  uint32_t push_seq;           // 0: do not push; else export rows of y go to the peers' buffer `out_buf` under this number
+  int out_buf;
+};
 void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const double *z, double *y, const double *scale_inv,
-                    double *store_scaled, double ca, double cb, double cg);
+                    double *store_scaled, double ca, double cb, double cg, const SpmvDist *dist = nullptr);
+// ---- row-partitioned mode (dist.cu) ------------------------------------------------------------------
+inline int dist_ranks(const eigkl_handle *h);                      // 1 = every rank solves the whole problem
+int64_t dist_decide(eigkl_handle *h);                             // assemble_laplacian: replicate or cut rows; local nnz
+void dist_plan(eigkl_handle *h);                                  // halo / export plan once the SpMV row blocks exist
+double *dist_buf(eigkl_handle *h, int b);                         // arena vector b (0..2 = w, 3 = stage), R x n_pad doubles
+inline double *dist_own(eigkl_handle *h, int b);
+uint32_t dist_push(eigkl_handle *h, int b);                       // push the own slot's export rows of buffer b; returns its seq
+void dist_stage_load(eigkl_handle *h, const double *src_local);   // stage.own = src (then dist_push(h, 3))
+void dist_check(eigkl_handle *h);                                 // throws when a flag wait timed out
+void dist_gather_full(eigkl_handle *h, const double *slice, double *full_natural);   // NCCL all-gather + un-slotting
+void peer_arena_destroy(eigkl_handle *h);
 void fiedler_solve(eigkl_handle *h);
 void partition_from_fiedler(eigkl_handle *h);
 void sym_eig(int n, double *a, double *evals);   // dense symmetric eigen-solver (host)
@@ -338,7 +403,8 @@ struct HostHgr {
 };
 void parse_hgr(const char *path, HostHgr &out);
 void write_eig_file(const char *path, double lambda2, double median, const double *vec, int32_t n);
-void read_eig_file(const char *path, int32_t n, std::vector<uint8_t> &side);
+void read_eig_file(const char *path, int32_t n, std::vector<uint8_t> &side, std::vector<int32_t> &order0,
+                   std::vector<int32_t> &order1, bool &ascending);
 void write_trace_file(const char *path, const eigkl_trace *t);
 
 // ---- comm (comm.cpp) --------------------------------------------------------------------------------------
@@ -349,8 +415,12 @@ void comm_allreduce_sum_f64(eigkl_handle *h, double *buf, size_t count);        
 void comm_allreduce_max_u64(eigkl_handle *h, unsigned long long *buf, size_t count);
 void comm_allgather_f64(eigkl_handle *h, const double *send, double *recv, size_t count_per_rank);
 void comm_broadcast_bytes(eigkl_handle *h, void *buf, size_t bytes, int root);
+void comm_allgather_bytes(eigkl_handle *h, const void *send, void *recv, size_t bytes_per_rank);
+void comm_allreduce_min_i32(eigkl_handle *h, int32_t *buf, size_t count);
 
 inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+inline int dist_ranks(const eigkl_handle *h) { return h->dist.valid ? h->dist.R : 1; }
+inline double *dist_own(eigkl_handle *h, int b) { return dist_buf(h, b) + (size_t)h->dist.me * (size_t)h->dist.n_pad; }
 
 // 1-D row partition of n rows over nranks ranks: equal blocks of n_pad rows (a multiple of 32, so that
 // one ncclAllGather of n_pad values per rank rebuilds a full vector in place: global row g lives at

@@ -126,11 +126,31 @@ dvalues_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ c
   }
 }
 
+// After a pass, state[] holds lock bits and the swapped sides while order0 / order1 / rank / n0 / n1 still
+// describe the partition the pass started from.  The reference's KL() rebuilds remain[] / split[] from the current
+// sides on every call (cKL.cpp:290-301), so the next pass / cut / D-value request does the same here: the final
+// sides become a fresh partition with ascending remain[] lists and no locks.
+__global__ void mask_side_kernel(const uint8_t *__restrict__ state, int32_t n, uint8_t *__restrict__ out) {
+  int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v < n) out[v] = state[v] & ST_SIDE;
+}
+void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev);
+static void kl_rearm(eigkl_handle *h) {
+  auto &k = h->kl;
+  if (!k.have_partition || !k.consumed) return;
+  const int32_t n = h->hg.n_nodes;
+  auto &side = h->scr.u8a; side.alloc((size_t)n);
+  mask_side_kernel<<<grid_for(n), TPB, 0, h->stream>>>(k.state.p, n, side.p);
+  h->launches++;
+  kl_set_partition_device(h, side.p);
+}
+
 void kl_dvalues(eigkl_handle *h) {
   auto &A = h->A;
   auto &k = h->kl;
   EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "KL graph not assembled");
   EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "no partition set");
+  kl_rearm(h);
   h->prof.begin(KC_DVALUES, h->stream);
   dvalues_kernel<<<(unsigned)A.n_blocks, KLD_THREADS, 0, h->stream>>>(A.rowptr.p, A.col.p, A.w.p, k.state.p, k.val.p, A.blk_row.p);
   h->prof.end(h->stream);
@@ -195,7 +215,7 @@ void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
   EIGKL_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   EIGKL_REQUIRE(herr == 0, EIGKL_E_FORMAT, "partition side not in {0,1}");
-  k.n0 = n0; k.n1 = n - n0; k.ascending = true; k.have_partition = true;
+  k.n0 = n0; k.n1 = n - n0; k.ascending = true; k.have_partition = true; k.consumed = false;
 }
 
 void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *order0, int64_t n0,
@@ -225,7 +245,7 @@ void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *
   EIGKL_CUDA(cudaMemcpyAsync(&herr, err.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   EIGKL_REQUIRE(herr == 0, EIGKL_E_ARG, "orders must cover every node exactly once");
-  k.n0 = n0; k.n1 = n1; k.ascending = false; k.have_partition = true;
+  k.n0 = n0; k.n1 = n1; k.ascending = false; k.have_partition = true; k.consumed = false;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -312,6 +332,7 @@ float kl_cut0(eigkl_handle *h) {
   auto &e = h->eig;
   EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "KL graph not assembled");
   EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "no partition set");
+  kl_rearm(h);
   const int32_t n = A.n;
   const int32_t n1 = (int32_t)k.n1;
   cudaStream_t st = h->stream;
@@ -973,6 +994,7 @@ void kl_run(eigkl_handle *h) {
   auto &k = h->kl;
   EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "eigkl_kl_run: call eigkl_assemble_kl_graph first");
   EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "eigkl_kl_run: no initial partition");
+  kl_rearm(h);
   const int32_t n = A.n;
   cudaStream_t st = h->stream;
   const int64_t cap = std::min(k.n0, k.n1) + 1;
@@ -983,7 +1005,10 @@ void kl_run(eigkl_handle *h) {
   const float cut0 = kl_cut0(h);                                     // cKL.cpp:306
   kl_dvalues(h);                                                     // cKL.cpp:318-321
   const int32_t n_tiles = (int32_t)ceil_div(n, KL_TILE);
-  const int R = h->opts.nranks;
+  // Several ranks: the pass is latency-bound and sequential (one CTA at 4.4 us per swap), so every rank runs the
+  // complete pass on its own replica -- bit-identical by construction.  EIGKL_KL_DIST=1 keeps the partitioned
+  // variant (D-values / tile keys by node range, one NCCL arg-max all-reduce per swap: 24 us per swap measured).
+  const int R = h->kl_dist ? h->opts.nranks : 1;
   int32_t own_lo = 0, own_hi = n, own_pad = 0;
   if (R > 1) row_partition(n, R, h->opts.rank, &own_lo, &own_hi, &own_pad);
   // state in shared memory (one CTA) whenever it fits, unless a cluster size was asked for explicitly
@@ -1104,6 +1129,7 @@ void kl_run(eigkl_handle *h) {
   h->stats.ms_kl_loop = h->timer.ms();
   EIGKL_REQUIRE(ctrl[1] == 1, EIGKL_E_CUDA, "KL kernel did not complete");
   k.swaps = ctrl[0];
+  k.consumed = true;
   h->stats.kl_swaps = k.swaps;
   if (getenv("EIGKL_KL_PHASES") && R == 1 && !local && k.swaps > 0) {   // the global-memory loop carries the clocks
     static const char *nm[6] = {"S1 reduce", "decode", "S3 own rows", "S3 barrier wait", "S4 own tiles", "S4 barrier wait"};

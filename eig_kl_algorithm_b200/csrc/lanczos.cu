@@ -529,6 +529,43 @@ __global__ void unpermute_kernel(const double *__restrict__ in, const int32_t *_
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[perm[i]] = in[i];
 }
+// Canonical sign of the returned vector: the component of largest magnitude (lowest file id on ties) is made
+// positive.  An eigenvector's sign is arbitrary (the reference returns whatever Spectra produced);
+// fixing it makes the fused EIG -> KL pipeline reproducible across seeds and rank counts (the side labels, and
+// with them the last digits of the fp32 initial cut, follow the sign).  One CTA, once per solve.
+__global__ void __launch_bounds__(1024) canonical_sign_kernel(double *__restrict__ v, int32_t n) {
+  __shared__ double bm[32];
+  __shared__ int32_t bi[32];
+  __shared__ int flip;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double best = -1.0;
+  int32_t idx = 0x7fffffff;
+  for (int32_t i = tid; i < n; i += 1024) {
+    const double a = fabs(v[i]);
+    if (a > best) { best = a; idx = i; }               // ascending i per thread: first maximum
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double ob = __shfl_xor_sync(FULL_MASK, best, o);
+    const int32_t oi = __shfl_xor_sync(FULL_MASK, idx, o);
+    if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+  }
+  if (lane == 0) { bm[warp] = best; bi[warp] = idx; }
+  __syncthreads();
+  if (warp == 0) {
+    best = bm[lane]; idx = bi[lane];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ob = __shfl_xor_sync(FULL_MASK, best, o);
+      const int32_t oi = __shfl_xor_sync(FULL_MASK, idx, o);
+      if (ob > best || (ob == best && oi < idx)) { best = ob; idx = oi; }
+    }
+    if (lane == 0) flip = (idx < n && v[idx] < 0.0) ? 1 : 0;
+  }
+  __syncthreads();
+  if (flip)
+    for (int32_t i = tid; i < n; i += 1024) v[i] = -v[i];
+}
 __global__ void scale_store_kernel(const double *__restrict__ w, const double *__restrict__ scale, double *__restrict__ out, int32_t n) {
   int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = w[i] * __ldg(scale);
@@ -619,7 +656,11 @@ void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, doub
   } else {
     EIGKL_CUDA(cudaMemsetAsync(h_out, 0, (size_t)ncols * sizeof(double), c.h->stream));
   }
-  if (c.R > 1) comm_allreduce_sum_f64(c.h, h_out, (size_t)ncols);      // C2: Lanczos dot products
+  if (c.R > 1) {                                                       // C2: Lanczos dot products
+    c.h->prof.begin(KC_COMM, c.h->stream);
+    comm_allreduce_sum_f64(c.h, h_out, (size_t)ncols);
+    c.h->prof.end(c.h->stream);
+  }
 }
 void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double *hcoef, const double *h_prev, int j, int pass) {
   auto &e = c.h->eig;
@@ -644,7 +685,9 @@ void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double
     EIGKL_CUDA(cudaMemsetAsync(e.scal.p, 0, sizeof(double), c.h->stream));
   }
   if (!single) {
+    c.h->prof.begin(KC_COMM, c.h->stream);
     comm_allreduce_sum_f64(c.h, e.scal.p, 1);
+    c.h->prof.end(c.h->stream);
     if (pass == 1) decide_kernel<<<1, LZ_THREADS, 0, c.h->stream>>>(e.scal.p, hcoef, ncols, c.eta2, e.flag.p, e.beta.p, e.alpha.p, j);
     else beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, e.beta.p, e.alpha.p, h_prev, hcoef, j, e.flag.p);
     c.h->launches++;
@@ -681,7 +724,7 @@ void orthogonalise(LzCtx &c, double *V, int j, double *w) {
     cfg.dynamicSmemBytes = c.gs_smem;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeCooperative;     // the CTAs wait for each other at the two grid barriers
-    attr[0].val.cooperative = c.h->coop_launch ? 1 : 0;
+    attr[0].val.cooperative = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
     c.h->prof.begin(KC_MULTIDOT, c.h->stream);
     EIGKL_CUDA(cudaLaunchKernelEx(&cfg, gs_fused_kernel, A));
@@ -697,13 +740,6 @@ void orthogonalise(LzCtx &c, double *V, int j, double *w) {
   launch_update(c, V, j + 1, w, h1, nullptr, j, 1);      // sets flag = 1 when the second pass can be skipped
   launch_multidot(c, V, j + 1, w, h2, 2);
   launch_update(c, V, j + 1, w, h2, h1, j, 2);
-}
-
-// gather source for an SpMV whose input is the rank-local slice xl
-const double *gathered(LzCtx &c, const double *xl) {
-  if (c.R == 1) return xl;
-  comm_allgather_f64(c.h, xl, c.h->eig.xfull.p, c.ld);                 // C1: SpMV halo exchange
-  return c.h->eig.xfull.p - 0;
 }
 
 }  // namespace
@@ -733,10 +769,11 @@ void fiedler_solve(eigkl_handle *h) {
   cudaStream_t st = h->stream;
 
   LzCtx c;
-  c.h = h; c.n = n; c.m = m; c.R = h->opts.nranks;
-  int32_t lo, hi, n_pad;
-  row_partition(n, c.R, h->opts.rank, &lo, &hi, &n_pad);
-  EIGKL_REQUIRE(lo == L.row_lo && hi == L.row_hi, EIGKL_E_ARG, "row partition changed since assembly");
+  // one rank, or several ranks each solving the whole (chip-resident) problem: R = 1; row-partitioned: R = nranks
+  c.h = h; c.n = n; c.m = m; c.R = dist_ranks(h);
+  const bool dist = c.R > 1;
+  const int32_t lo = L.row_lo, hi = L.row_hi;
+  const int32_t n_pad = dist ? h->dist.n_pad : (int32_t)(ceil_div(n, 32) * 32);
   c.nl = hi - lo; c.row_lo = lo;
   c.ld = (size_t)n_pad;
   c.gx_md = (int)std::max<int64_t>(1, ceil_div(c.nl, MD_ROWS));
@@ -761,7 +798,12 @@ void fiedler_solve(eigkl_handle *h) {
 
   e.n = n; e.ncv = m; e.ld = c.ld;
   for (int b = 0; b < 2; ++b) e.V[b].ensure(c.ld * (size_t)(m + 7));
-  for (int b = 0; b < 3; ++b) e.w[b].ensure(c.ld);
+  // the three recurrence vectors: plain buffers, or (row-partitioned) this rank's slot of the peer-mapped x buffers
+  double *wl[3];
+  for (int b = 0; b < 3; ++b) {
+    if (dist) wl[b] = dist_own(h, b);
+    else { e.w[b].ensure(c.ld); wl[b] = e.w[b].p; }
+  }
   e.partial.ensure((size_t)std::max<int64_t>((int64_t)c.gx_md * (m + 1), c.gx_up) + 8);
   e.hcoef.ensure(2 * (size_t)(m + 1));
   e.alpha.ensure((size_t)m); e.beta.ensure((size_t)m);
@@ -774,9 +816,8 @@ void fiedler_solve(eigkl_handle *h) {
   e.fiedler.ensure((size_t)n);
   e.fiedler_perm.ensure(c.ld * (size_t)c.R);
   EIGKL_REQUIRE(h->order.valid, EIGKL_E_ARG, "node order missing");
-  if (c.R > 1) e.xfull.ensure(c.ld * (size_t)c.R);
   EIGKL_CUDA(cudaMemsetAsync(e.counters.p, 0, (size_t)n_counters * sizeof(unsigned int), st));
-  for (int b = 0; b < 3; ++b) EIGKL_CUDA(cudaMemsetAsync(e.w[b].p, 0, c.ld * sizeof(double), st));
+  for (int b = 0; b < 3; ++b) EIGKL_CUDA(cudaMemsetAsync(wl[b], 0, c.ld * sizeof(double), st));   // own rows only: halo slots belong to the peers
   const double one = 1.0;
   EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 2, &one, sizeof(double), cudaMemcpyHostToDevice, st));   // scal[2] = 1.0
   const double *d_one = e.scal.p + 2;
@@ -784,10 +825,10 @@ void fiedler_solve(eigkl_handle *h) {
   // start vector (Spectra: SimpleRandom residual, uniform in [-0.5, 0.5); ours is a seeded splitmix64 of the
   // GLOBAL row id, so the vector does not depend on the number of ranks)
   if (c.nl > 0) {
-    fill_random_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[0].p, c.nl, h->opts.seed + 0x9E3779B97F4A7C15ull, lo);
+    fill_random_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(wl[0], c.nl, h->opts.seed + 0x9E3779B97F4A7C15ull, lo);
     h->launches++;
   }
-  launch_norm(c, e.w[0].p);
+  launch_norm(c, wl[0]);
 
   // w = B x:  d SpMVs, recurrence fused.  x is either an un-normalised buffer (scale = 1/beta, v_j stored)
   // or an already normalised basis column (after a restart).  Returns the index of the buffer holding w.
@@ -830,6 +871,30 @@ void fiedler_solve(eigkl_handle *h) {
     // ~2 us an event pair costs is not charged to every 15 us launch
     const bool group = h->prof.on && c.R == 1;
     int o1 = (avoid + 1) % 3;
+    if (dist) {
+      // row-partitioned: the input's export rows are pushed to the peers by a small kernel (x comes out of the
+      // Gram-Schmidt kernels); every later SpMV of the chain receives its halo from the epilogue of the one before
+      int xb = -1;
+      for (int b = 0; b < 3; ++b)
+        if (x_in == wl[b]) xb = b;
+      if (xb < 0) { dist_stage_load(h, x_in); xb = 3; }             // a basis column (after a restart)
+      uint32_t have = dist_push(h, xb);
+      SpmvDist d{have, deg > 1 ? ++h->arena.seq : 0u, o1};
+      spmv_launch_ex(h, dist_buf(h, xb), dist_own(h, xb), nullptr, wl[o1], scale, v_store, -1.0 / fe, fc / fe, 0.0, &d);
+      have = d.push_seq;
+      const double *prev2 = v_norm;
+      int p1 = o1;
+      for (int kk = 2; kk <= deg; ++kk) {
+        int o = 0;
+        while (o == p1 || wl[o] == prev2) ++o;
+        SpmvDist dk{have, kk < deg ? ++h->arena.seq : 0u, o};
+        spmv_launch_ex(h, dist_buf(h, p1), wl[p1], prev2, wl[o], d_one, nullptr, -2.0 / fe, 2.0 * fc / fe, -1.0, &dk);
+        have = dk.push_seq;
+        prev2 = wl[p1];
+        p1 = o;
+      }
+      return p1;
+    }
     if (resident) {
       // the whole recurrence in one cooperative launch (spmv.cu); same buffer rotation as below
       unsigned char out_idx[64];
@@ -841,7 +906,7 @@ void fiedler_solve(eigkl_handle *h) {
         out_idx[kk - 1] = (unsigned char)o;
         p2 = p1; p1 = o;
       }
-      double *wp[3] = {e.w[0].p, e.w[1].p, e.w[2].p};
+      double *wp[3] = {wl[0], wl[1], wl[2]};
       h->prof.begin(KC_SPMV, st, deg);
       cheb_resident_launch(h, x_in, scale, v_store, wp, out_idx, deg, fc, fe);
       h->prof.end(st);
@@ -849,15 +914,15 @@ void fiedler_solve(eigkl_handle *h) {
     }
     if (group) { h->prof.begin(KC_SPMV, st, deg); h->prof.suppress++; }
     // y1 = s * (c x - L x) / e
-    spmv_launch_ex(h, gathered(c, x_in), x_in, nullptr, e.w[o1].p, scale, v_store, -1.0 / fe, fc / fe, 0.0);
+    spmv_launch_ex(h, x_in, x_in, nullptr, wl[o1], scale, v_store, -1.0 / fe, fc / fe, 0.0);
     const double *prev2 = v_norm;            // normalised v_j (= T_0 x)
     int p1 = o1;
     for (int kk = 2; kk <= deg; ++kk) {
       int o = 0;
-      while (o == p1 || e.w[o].p == prev2) ++o;
+      while (o == p1 || wl[o] == prev2) ++o;
       // y_k = 2 (c y_{k-1} - L y_{k-1}) / e - y_{k-2}
-      spmv_launch_ex(h, gathered(c, e.w[p1].p), e.w[p1].p, prev2, e.w[o].p, d_one, nullptr, -2.0 / fe, 2.0 * fc / fe, -1.0);
-      prev2 = e.w[p1].p;
+      spmv_launch_ex(h, wl[p1], wl[p1], prev2, wl[o], d_one, nullptr, -2.0 / fe, 2.0 * fc / fe, -1.0);
+      prev2 = wl[p1];
       p1 = o;
     }
     if (group) { h->prof.suppress--; h->prof.end(st); }
@@ -956,7 +1021,13 @@ void fiedler_solve(eigkl_handle *h) {
     double H[4] = {0, 0, 0, 0};
     for (int t = 0; t < 2; ++t) {
       const double *xt = Vn + (size_t)t * c.ld;
-      spmv_launch_ex(h, gathered(c, xt), xt, nullptr, Vn + (size_t)(2 + t) * c.ld, d_one, nullptr, 1.0, 0.0, 0.0);
+      if (dist) {
+        dist_stage_load(h, xt);
+        SpmvDist d{dist_push(h, 3), 0u, 0};
+        spmv_launch_ex(h, dist_buf(h, 3), dist_own(h, 3), nullptr, Vn + (size_t)(2 + t) * c.ld, d_one, nullptr, 1.0, 0.0, 0.0, &d);
+      } else {
+        spmv_launch_ex(h, xt, xt, nullptr, Vn + (size_t)(2 + t) * c.ld, d_one, nullptr, 1.0, 0.0, 0.0);
+      }
       launch_multidot(c, Vn, 2, Vn + (size_t)(2 + t) * c.ld, e.hcoef.p, 1);
       EIGKL_CUDA(cudaMemcpyAsync(&H[2 * t], e.hcoef.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
       ++nmv;
@@ -994,7 +1065,7 @@ void fiedler_solve(eigkl_handle *h) {
         h->launches++;
       }
     }
-    if (c.R > 1) comm_allgather_f64(h, slice, e.fiedler_perm.p, c.ld);     // every rank ends with the full vector
+    if (c.R > 1) dist_gather_full(h, slice, e.fiedler_perm.p);             // every rank ends with the full vector
     unpermute_kernel<<<(unsigned)ceil_div(n, LZ_THREADS), LZ_THREADS, 0, st>>>(e.fiedler_perm.p, h->order.perm.p, e.fiedler.p, n);
     h->launches++;
     EIGKL_CUDA(cudaMemcpyAsync(e.scal.p + 1, e.scal.p + 4, sizeof(double), cudaMemcpyDeviceToDevice, st));
@@ -1009,10 +1080,10 @@ void fiedler_solve(eigkl_handle *h) {
     for (int j = k; j < m && !cycle_done; ++j) {
       int wi;
       if (j == k && it > 0) wi = apply_filter(V + (size_t)k * c.ld, d_one, nullptr, V + (size_t)k * c.ld, cur);   // normalised v_k
-      else wi = apply_filter(e.w[cur].p, e.scal.p + 1, V + (size_t)j * c.ld, V + (size_t)j * c.ld, cur);
+      else wi = apply_filter(wl[cur], e.scal.p + 1, V + (size_t)j * c.ld, V + (size_t)j * c.ld, cur);
       nmv += deg;
       cur = wi;
-      orthogonalise(c, V, j, e.w[cur].p);
+      orthogonalise(c, V, j, wl[cur]);
       const int jj = j + 1;
       const bool at_end = (jj == m);
       // accept when the pair is a genuine eigenpair of L (the reference's criterion is the same
@@ -1021,8 +1092,10 @@ void fiedler_solve(eigkl_handle *h) {
         jfin = cj - 1;
         true_res = extract(cj);
         const double accept = std::max(1e-9 * std::fabs(lam2), 1e-13 * fb);
-        if (true_res <= accept || tol_p < 1e-15) { converged = true; cycle_done = true; }
-        else tol_p *= 1e-2;
+        // only a pair whose TRUE residual passes is reported as converged; at the floor of the filtered
+        // tolerance the iteration simply goes on (more restarts) until max_restarts -> EIGKL_E_NOCONV
+        if (true_res <= accept) { converged = true; cycle_done = true; }
+        else if (tol_p > 1e-15) tol_p *= 1e-2;
       };
       // a posted check is evaluated `lag` steps later (always by the end of the cycle): one step covers the
       // tridiagonal solve of the first cycle (~30 us), two cover the arrowhead solve of the later ones (~150 us)
@@ -1060,7 +1133,7 @@ void fiedler_solve(eigkl_handle *h) {
       sym_top_eig(m, T.data(), kk, theta.data(), Ycm.data());
       // v_m = w / beta_m into column m
       if (c.nl > 0) {
-        scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(e.w[cur].p, e.scal.p + 1, V + (size_t)m * c.ld, c.nl);
+        scale_store_kernel<<<(unsigned)ceil_div(c.nl, LZ_THREADS), LZ_THREADS, 0, st>>>(wl[cur], e.scal.p + 1, V + (size_t)m * c.ld, c.nl);
         h->launches++;
       }
       EIGKL_CUDA(cudaMemcpyAsync(e.Y.p, Ycm.data(), Ycm.size() * sizeof(double), cudaMemcpyHostToDevice, st));
@@ -1089,6 +1162,9 @@ void fiedler_solve(eigkl_handle *h) {
     check(jfin + 1);
     true_res = extract(jfin + 1);
   }
+  canonical_sign_kernel<<<1, 1024, 0, st>>>(e.fiedler.p, n);
+  h->launches++;
+  dist_check(h);
   EIGKL_CUDA(cudaGetLastError());
   e.lambda2 = lam2;
   e.have_vector = true;

@@ -260,6 +260,140 @@ spmv_flat_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
 
 
 // ---------------------------------------------------------------------------------------------------
+// Row-partitioned SpMV with the halo exchange fused in (multi-GPU, dist.cu explains the layout).
+// The flat kernel above, with three changes:
+//   * the gather source is this rank's x buffer (own rows + packed halos), indexed by the pre-computed col_c;
+//   * after its constant prologue (and the dependent-launch wait) a CTA polls this rank's flags until every peer's
+//     push of the input vector (number wait_seq) has landed -- peers write the halo slots over NVLink;
+//   * the epilogue keeps the block's y values in shared memory and one warp per peer copies the block's segment of
+//     that peer's export list straight into the peer's slot `me` of the OUTPUT buffer (packed, coalesced 8-byte
+//     stores through the peer mapping); the last CTA to finish raises this rank's flag on every peer (release at
+//     system scope).  Compute, transfer and signalling are one kernel; values that nobody needs never travel.
+// ---------------------------------------------------------------------------------------------------
+struct DistArgs {
+  const int32_t *col_c;
+  int32_t e_lo;
+  const unsigned int *flags;           // this rank's flags: flags[p] = last production rank p has pushed completely
+  const unsigned long long *peers;     // arena base of every rank in this process' address space
+  size_t out_off;                      // byte offset of the output vector inside an arena
+  const int32_t *exp_ids, *blk_exp;
+  int32_t n_pad;
+  int me, R;
+  uint32_t wait_seq, push_seq;
+  unsigned int *ticket;
+  int *err;
+};
+
+__device__ __forceinline__ void dist_wait_flags(const DistArgs &D) {
+  if (threadIdx.x < (unsigned)D.R && (int)threadIdx.x != D.me) {
+    const unsigned int *f = D.flags + threadIdx.x;
+    unsigned int v;
+    const long long t0 = clock64();
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(f) : "memory");
+      if ((int)(v - D.wait_seq) >= 0) break;
+      if (clock64() - t0 > 6000000000ll) { atomicExch(D.err, 1); break; }      // ~3 s: ranks out of step; reported by dist_check
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(SPMV_THREADS, 4)
+spmv_dist_kernel(const int32_t *__restrict__ rowptr, const double *__restrict__ val, const double *x, const double *xl,
+                 const double *__restrict__ z, double *__restrict__ y, const int4 *__restrict__ blk_info,
+                 const double *__restrict__ scale, double *__restrict__ v_store, int32_t row_offset, double ca, double cb,
+                 double cg, const DistArgs D) {
+  __shared__ double prod[FLAT_CAP];
+  __shared__ double ys[FLAT_CAP];
+  __shared__ int32_t rp[FLAT_CAP + 1];
+  __shared__ int32_t long_rows[SPMV_MAX_LONG];
+  __shared__ int n_long;
+  __shared__ bool am_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  asm volatile("griddepcontrol.launch_dependents;");
+  const int4 info = __ldg(blk_info + blockIdx.x);
+  const int32_t r0 = info.x, r1 = info.y, e0 = info.z, e1 = info.w;
+  const int32_t span = e1 - e0, nrows = r1 - r0;
+  const bool flat = nrows > 0 && span <= FLAT_CAP;
+  double a[FLAT_K];
+  int32_t c[FLAT_K];
+  if (flat) {
+#pragma unroll
+    for (int k = 0; k < FLAT_K; ++k) {
+      const int32_t i = tid + k * SPMV_THREADS;
+      a[k] = 0.0; c[k] = -1;
+      if (i < span) { a[k] = __ldcs(val + e0 + i); c[k] = __ldcs(D.col_c + (e0 - D.e_lo) + i); }
+    }
+    for (int32_t rr = tid; rr <= nrows; rr += SPMV_THREADS) rp[rr] = rowptr[r0 + rr] - e0;
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  dist_wait_flags(D);
+  const double sc = scale ? __ldg(scale) : 1.0;
+  const SpmvEpilogue ep{xl, z, y, ca * sc, cb * sc, cg, row_offset};
+  if (flat) {
+    double pre0 = 0.0, xs0 = 0.0;
+    if (tid < nrows) {
+      pre0 = ep.prefetch(r0 + tid);
+      if (v_store) xs0 = xl[r0 + tid - row_offset] * sc;
+    }
+#pragma unroll
+    for (int k = 0; k < FLAT_K; ++k) {
+      const int32_t i = tid + k * SPMV_THREADS;
+      if (c[k] >= 0) prod[i] = a[k] * __ldcg(x + c[k]);            // halo slots are written by peers: L2 is the coherence point
+    }
+    __syncthreads();
+    for (int32_t rr = tid; rr < nrows; rr += SPMV_THREADS) {
+      const int32_t lo = rp[rr], hi = rp[rr + 1];
+      double s0 = 0.0, s1 = 0.0;
+      int32_t i = lo;
+      for (; i + 1 < hi; i += 2) { s0 += prod[i]; s1 += prod[i + 1]; }
+      if (i < hi) s0 += prod[i];
+      const int32_t r = r0 + rr;
+      const double yv = ep.ca * (s0 + s1) + (rr == tid ? pre0 : ep.prefetch(r));
+      y[r - row_offset] = yv;
+      ys[rr] = yv;
+      if (v_store) v_store[r - row_offset] = (rr == tid) ? xs0 : xl[r - row_offset] * sc;
+    }
+  } else if (nrows > 0) {                                         // a row too long for the staging buffer lives here
+    if (v_store)
+      for (int32_t r = r0 + tid; r < r1; r += SPMV_THREADS) v_store[r - row_offset] = xl[r - row_offset] * sc;
+    // the sub-warp routine gathers through the read-only path with the ORIGINAL column ids: not usable on the
+    // packed buffer, so this (rare) block walks its rows warp by warp over col_c
+    for (int32_t r = r0 + warp; r < r1; r += SPMV_THREADS / 32) {
+      const int32_t lo = rowptr[r], hi = rowptr[r + 1];
+      double s = 0.0;
+      for (int32_t i = lo + lane; i < hi; i += 32) s += __ldcs(val + i) * __ldcg(x + __ldcs(D.col_c + (i - D.e_lo)));
+      s = warp_sum(s);
+      if (lane == 0) ep.emit(r, s);
+    }
+  }
+  (void)long_rows; (void)n_long;
+  if (D.push_seq == 0) return;
+  __syncthreads();
+  // ---- push this block's export rows: warp w serves peers w, w + 8, ... ----
+  for (int q = warp; q < D.R; q += SPMV_THREADS / 32) {
+    if (q == D.me) continue;
+    const int32_t s = D.blk_exp[(size_t)blockIdx.x * D.R + q], e = D.blk_exp[(size_t)(blockIdx.x + 1) * D.R + q];
+    double *dst = reinterpret_cast<double *>(D.peers[q] + D.out_off) + (size_t)D.me * D.n_pad;
+    const int32_t *ids = D.exp_ids + (size_t)q * D.n_pad;
+    for (int32_t i = s + lane; i < e; i += 32) {
+      const int32_t rl = ids[i];                                   // local row offset
+      dst[i] = flat ? ys[rl - (r0 - row_offset)] : __ldcg(y + rl);
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (tid == 0) am_last = (atomicInc(D.ticket, gridDim.x - 1) == gridDim.x - 1);
+  __syncthreads();
+  if (!am_last) return;
+  __threadfence_system();
+  if (tid < D.R && tid != D.me) {
+    unsigned int *flag = reinterpret_cast<unsigned int *>(D.peers[tid]) + D.me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(D.push_seq) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Resident polynomial filter: the d SpMVs of one Chebyshev filter application as ONE cooperative launch.
 //
 // On the shipped circuits a SpMV launch is ~8 us of which the bytes explain ~3: the rest is launch/drain and
@@ -599,7 +733,8 @@ void cheb_resident_plan(eigkl_handle *h) {
   L.res_k = 0;
   // a row is charged like one more entry, so that a block never holds more rows than half its entry capacity
   const int64_t cost = L.nnz + (int64_t)n;
-  if (h->opts.nranks != 1 || !h->spmv_resident || n > PLAN_MAX_N || cost > (int64_t)(RES_CAP - 1) * h->sm_count) return;
+  // with several ranks the plan is still made: a matrix that fits the chip is solved replicated on every rank
+  if ((h->opts.nranks != 1 && h->dist_mode == 1) || !h->spmv_resident || n > PLAN_MAX_N || cost > (int64_t)(RES_CAP - 1) * h->sm_count) return;
   int64_t min_chunk = 1024;
   if (const char *ev = getenv("EIGKL_RES_CHUNK")) min_chunk = std::max<int64_t>(64, atoll(ev));   // tuning aid
   int64_t chunk = std::max<int64_t>(min_chunk, ceil_div(cost, (int64_t)h->sm_count));
@@ -658,7 +793,7 @@ void cheb_resident_plan_finish(eigkl_handle *h) {
 }
 
 bool cheb_resident_usable(const eigkl_handle *h) {
-  return h->spmv_resident && h->opts.nranks == 1 && h->L.valid && h->L.res_ok;
+  return h->spmv_resident && !h->dist.valid && h->L.valid && h->L.res_ok;
 }
 
 void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *scale, double *v_store, double *const w[3],
@@ -685,7 +820,7 @@ void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *sca
   cfg.stream = h->stream;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeCooperative;       // every CTA resident at once: a CTA waits on its neighbours' values
-  attr[0].val.cooperative = h->coop_launch ? 1 : 0;
+  attr[0].val.cooperative = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   if (L.res_k == 4) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<4, 768>, A));
   else if (L.res_k == 8) EIGKL_CUDA(cudaLaunchKernelEx(&cfg, cheb_resident_kernel<8, 768>, A));
@@ -699,9 +834,39 @@ void cheb_resident_launch(eigkl_handle *h, const double *x_in, const double *sca
 //   xg: full-length x (global column ids, the gather source); xl: this rank's slice of the same vector;
 //   z, y, store_scaled: rank-local slices.
 void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const double *z, double *y, const double *scale_inv,
-                    double *store_scaled, double ca, double cb, double cg) {
+                    double *store_scaled, double ca, double cb, double cg, const SpmvDist *dist) {
   auto &L = h->L;
   EIGKL_REQUIRE(L.valid, EIGKL_E_ARG, "Laplacian not assembled");
+  if (h->dist.valid) {
+    // row-partitioned: launched even by a rank without rows, because the flag protocol counts every rank
+    EIGKL_REQUIRE(dist != nullptr && L.flat, EIGKL_E_ARG, "row-partitioned SpMV needs its exchange arguments");
+    auto &P = h->dist;
+    DistArgs D{};
+    D.col_c = P.col_c.p; D.e_lo = P.e_lo;
+    D.flags = reinterpret_cast<const unsigned int *>(h->arena.base);
+    D.peers = h->arena.dev_ptrs.p;
+    D.out_off = PEER_FLAGS_BYTES + (size_t)dist->out_buf * h->arena.vec_bytes;
+    D.exp_ids = P.exp_ids.p; D.blk_exp = P.blk_exp.p;
+    D.n_pad = P.n_pad; D.me = P.me; D.R = P.R;
+    D.wait_seq = dist->wait_seq; D.push_seq = dist->push_seq;
+    D.ticket = h->arena.ticket.p + 1; D.err = h->arena.err.p;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)L.n_blocks);
+    cfg.blockDim = dim3(SPMV_THREADS);
+    cfg.stream = h->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = h->spmv_pdl ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    const int4 *info = reinterpret_cast<const int4 *>(L.blk_info.p);
+    const int32_t *rp = L.rowptr.p;
+    const double *vl = L.val.p;
+    h->prof.begin(KC_SPMV, h->stream);
+    EIGKL_CUDA(cudaLaunchKernelEx(&cfg, spmv_dist_kernel, rp, vl, xg, xl, z, y, info, scale_inv, store_scaled, L.row_lo, ca, cb, cg, D));
+    h->prof.end(h->stream);
+    h->launches++;
+    return;
+  }
   if (L.row_hi <= L.row_lo) return;
   h->prof.begin(KC_SPMV, h->stream);
   const bool with_stream = h->spmv_mode == 1 || (h->spmv_mode == 0 && L.nnz < 6 * (int64_t)L.n);

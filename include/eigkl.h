@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define EIGKL_ABI_VERSION 1
+#define EIGKL_ABI_VERSION 2
 
 enum {
   EIGKL_OK        = 0,
@@ -96,6 +96,14 @@ typedef struct {
   int32_t  kl_local;             /* swap loop as one CTA: 1 = tile keys and side bits in shared memory, 2 = tile keys
                                   * in shared memory and state bytes in global memory; 0 = global-memory cluster kernel */
   int32_t  reserved0;
+  /* multi-rank Lanczos (nranks > 1): 1 = every rank solved the whole problem (the matrix fits one chip), R = rows
+   * partitioned over R ranks; then this rank's rows, the halo values it receives and the rows it pushes per SpMV */
+  int32_t  dist_ranks, dist_rows;
+  int64_t  dist_halo, dist_exports;
+  /* only with profiling on, row-partitioned mode: the NCCL all-reduces of the Lanczos dot products / norms, and the
+   * stand-alone halo pushes (one per filter application; the other pushes ride inside the SpMV kernel)            */
+  double   ms_comm, ms_push;
+  int64_t  n_comm, n_push;
 } eigkl_stats;
 
 /* KL trace, one row per swap plus row 0 (the initial cut) -- the rows cKL writes to
@@ -118,6 +126,9 @@ void eigkl_destroy(eigkl_handle *h);
 const char *eigkl_last_error(const eigkl_handle *h);   /* h may be NULL: error of a failed create */
 int  eigkl_get_stats(const eigkl_handle *h, eigkl_stats *out);
 int  eigkl_synchronize(eigkl_handle *h);
+/* switches the per-kernel-class event brackets (EIGKL_F_PROFILE) on or off for the calls that follow, and clears
+ * the per-class sums.  With several ranks every rank must switch alike.                                          */
+int  eigkl_set_profile(eigkl_handle *h, int on);
 
 /* ---- input: the hypergraph ------------------------------------------------------------------- */
 /* Parses a .hgr file: header "<nets> <nodes>", then <nets> lines of 1-based pin ids.

@@ -328,13 +328,64 @@ static float orc_edge_weight(const orc_klgraph *g, int32_t a, int32_t b) {
   return 0.0f;
 }
 
-/* KL(), cKL.cpp:288-390: one pass, no rollback */
-int64_t orc_kl_run(const orc_klgraph *g, uint8_t *side,
-                   const int32_t *order0, int64_t n0, const int32_t *order1, int64_t n1,
-                   float *cut, float *gain, int32_t *node1, int32_t *node2, int64_t capacity) {
+/* KL(), cKL.cpp:288-390: one pass, no rollback.
+ *
+ * Pair selection (cKL.cpp:337-355) is "first strictly greatest val over remain[0] in order" / "first
+ * strictly smallest over remain[1]".  orc_kl_run_linear does literally that, O(|remain|) per swap -- fine up
+ * to ibm10, hopeless at 2 M nodes (5e11 comparisons per pass).  orc_kl_run keeps, per block of ORC_SEL_BLOCK
+ * consecutive POSITIONS of remain[s], the first best element of the block and rescans a block only when one of
+ * its nodes changed value or was locked since the last selection; the winner is the first block (in position
+ * order) holding the strictly best block value -- the same element the linear scan returns, by construction
+ * (tests/test_oracle.py checks the two against each other and against the reference's traces).            */
+#define ORC_SEL_BLOCK 256
+typedef struct {
+  const int32_t *order; int64_t n; int64_t nb;
+  float *bval; int64_t *bidx; uint8_t *dirty;
+} orc_sel;
+static void sel_init(orc_sel *s, const int32_t *order, int64_t n) {
+  s->order = order; s->n = n; s->nb = (n + ORC_SEL_BLOCK - 1) / ORC_SEL_BLOCK;
+  s->bval = (float *)malloc((size_t)(s->nb ? s->nb : 1) * sizeof(float));
+  s->bidx = (int64_t *)malloc((size_t)(s->nb ? s->nb : 1) * sizeof(int64_t));
+  s->dirty = (uint8_t *)malloc((size_t)(s->nb ? s->nb : 1));
+  memset(s->dirty, 1, (size_t)(s->nb ? s->nb : 1));
+}
+static void sel_free(orc_sel *s) { free(s->bval); free(s->bidx); free(s->dirty); }
+/* want_max: first strictly greatest; else first strictly smallest.  Returns the position or -1. */
+static int64_t sel_pick(orc_sel *s, const float *val, const uint8_t *locked, int want_max, float *best_out) {
+  float best = want_max ? -FLT_MAX : FLT_MAX;
+  int64_t best_i = -1;
+  for (int64_t b = 0; b < s->nb; ++b) {
+    if (s->dirty[b]) {
+      float bv = want_max ? -FLT_MAX : FLT_MAX;
+      int64_t bi = -1;
+      const int64_t hi = (b + 1) * ORC_SEL_BLOCK < s->n ? (b + 1) * ORC_SEL_BLOCK : s->n;
+      for (int64_t i = b * ORC_SEL_BLOCK; i < hi; ++i) {
+        const int32_t v = s->order[i];
+        if (locked[v]) continue;
+        if (want_max ? (val[v] > bv) : (val[v] < bv)) { bv = val[v]; bi = i; }
+      }
+      s->bval[b] = bv; s->bidx[b] = bi; s->dirty[b] = 0;
+    }
+    if (s->bidx[b] >= 0 && (want_max ? (s->bval[b] > best) : (s->bval[b] < best))) { best = s->bval[b]; best_i = s->bidx[b]; }
+  }
+  *best_out = best;
+  return best_i;
+}
+
+static int64_t orc_kl_run_impl(const orc_klgraph *g, uint8_t *side,
+                               const int32_t *order0, int64_t n0, const int32_t *order1, int64_t n1,
+                               float *cut, float *gain, int32_t *node1, int32_t *node2, int64_t capacity, int linear) {
   const int32_t n = g->n;
   float *val = (float *)malloc((size_t)(n ? n : 1) * sizeof(float));
   uint8_t *locked = (uint8_t *)calloc((size_t)(n ? n : 1), 1);
+  int64_t *pos = NULL;                                             /* position of a node in its remain[] list */
+  orc_sel s0, s1;
+  if (!linear) {
+    pos = (int64_t *)malloc((size_t)(n ? n : 1) * sizeof(int64_t));
+    for (int64_t i = 0; i < n0; ++i) pos[order0[i]] = i;
+    for (int64_t i = 0; i < n1; ++i) pos[order1[i]] = i;
+    sel_init(&s0, order0, n0); sel_init(&s1, order1, n1);
+  }
   uint32_t terminate = 0;
   uint32_t terminateLimit = (uint32_t)log2((double)n) + 5;        /* cKL.cpp:303 */
   float cutSize = orc_kl_cut0(g, side, order0, n0, order1, n1);   /* cKL.cpp:306 */
@@ -346,15 +397,20 @@ int64_t orc_kl_run(const orc_klgraph *g, uint8_t *side,
   while (rem0 > 0 && rem1 > 0) {                                   /* cKL.cpp:334 */
     float maxGain = -FLT_MAX, minGain = FLT_MAX;
     int64_t maxIdx = -1, minIdx = -1;
-    while (lo0 < n0 && locked[order0[lo0]]) ++lo0;
-    while (lo1 < n1 && locked[order1[lo1]]) ++lo1;
-    for (int64_t i = lo0; i < n0; ++i) {                           /* cKL.cpp:341-347 */
-      int32_t v = order0[i];
-      if (!locked[v] && val[v] > maxGain) { maxGain = val[v]; maxIdx = i; }
-    }
-    for (int64_t i = lo1; i < n1; ++i) {                           /* cKL.cpp:349-355 */
-      int32_t v = order1[i];
-      if (!locked[v] && val[v] < minGain) { minGain = val[v]; minIdx = i; }
+    if (linear) {
+      while (lo0 < n0 && locked[order0[lo0]]) ++lo0;
+      while (lo1 < n1 && locked[order1[lo1]]) ++lo1;
+      for (int64_t i = lo0; i < n0; ++i) {                         /* cKL.cpp:341-347 */
+        int32_t v = order0[i];
+        if (!locked[v] && val[v] > maxGain) { maxGain = val[v]; maxIdx = i; }
+      }
+      for (int64_t i = lo1; i < n1; ++i) {                         /* cKL.cpp:349-355 */
+        int32_t v = order1[i];
+        if (!locked[v] && val[v] < minGain) { minGain = val[v]; minIdx = i; }
+      }
+    } else {
+      maxIdx = sel_pick(&s0, val, locked, 1, &maxGain);
+      minIdx = sel_pick(&s1, val, locked, 0, &minGain);
     }
     if (maxIdx < 0 || minIdx < 0) break;                           /* cKL.cpp:387-389 */
     int32_t a = order0[maxIdx], b = order1[minIdx];
@@ -362,16 +418,39 @@ int64_t orc_kl_run(const orc_klgraph *g, uint8_t *side,
     cutSize -= gn;                                                 /* cKL.cpp:362 */
     locked[a] = 1; locked[b] = 1; --rem0; --rem1;                  /* swip, cKL.cpp:274-286 */
     side[a] = 1; side[b] = 0;
-    /* updateAffectedNodeGains, cKL.cpp:253-272: recompute N(a) u N(b) from scratch (incl. locked) */
-    for (int64_t e = g->rowptr[a]; e < g->rowptr[a + 1]; ++e) val[g->col[e]] = orc_connections(g, side, g->col[e]);
-    for (int64_t e = g->rowptr[b]; e < g->rowptr[b + 1]; ++e) val[g->col[e]] = orc_connections(g, side, g->col[e]);
+    if (!linear) { s0.dirty[maxIdx / ORC_SEL_BLOCK] = 1; s1.dirty[minIdx / ORC_SEL_BLOCK] = 1; }
+    /* updateAffectedNodeGains, cKL.cpp:253-272: recompute N(a) u N(b) from scratch (incl. locked).
+     * A node keeps its place in the remain[] list of the side it STARTED on (a and b are erased, nobody moves). */
+    for (int pass = 0; pass < 2; ++pass) {
+      const int32_t u = pass ? b : a;
+      for (int64_t e = g->rowptr[u]; e < g->rowptr[u + 1]; ++e) {
+        const int32_t v = g->col[e];
+        val[v] = orc_connections(g, side, v);
+        if (!linear && v != a && v != b) {
+          /* which list holds v: the side it had before this pass started = current side unless it was swapped
+           * (swapped nodes are locked and never selected again, so their block need not be refreshed) */
+          if (!locked[v]) { if (side[v] == 0) s0.dirty[pos[v] / ORC_SEL_BLOCK] = 1; else s1.dirty[pos[v] / ORC_SEL_BLOCK] = 1; }
+        }
+      }
+    }
     ++it;
     if (it < capacity) { cut[it] = cutSize; gain[it] = gn; node1[it] = a; node2[it] = b; }
     if (gn <= 0.0f) { if (++terminate > terminateLimit) break; }  /* cKL.cpp:382-386 */
     else terminate = 0;
   }
+  if (!linear) { sel_free(&s0); sel_free(&s1); free(pos); }
   free(val); free(locked);
   return it;
+}
+int64_t orc_kl_run(const orc_klgraph *g, uint8_t *side,
+                   const int32_t *order0, int64_t n0, const int32_t *order1, int64_t n1,
+                   float *cut, float *gain, int32_t *node1, int32_t *node2, int64_t capacity) {
+  return orc_kl_run_impl(g, side, order0, n0, order1, n1, cut, gain, node1, node2, capacity, 0);
+}
+int64_t orc_kl_run_linear(const orc_klgraph *g, uint8_t *side,
+                          const int32_t *order0, int64_t n0, const int32_t *order1, int64_t n1,
+                          float *cut, float *gain, int32_t *node1, int32_t *node2, int64_t capacity) {
+  return orc_kl_run_impl(g, side, order0, n0, order1, n1, cut, gain, node1, node2, capacity, 1);
 }
 
 /* ================================================================================================

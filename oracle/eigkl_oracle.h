@@ -57,6 +57,11 @@ float orc_kl_cut0(const orc_klgraph *g, const uint8_t *side,
 int64_t orc_kl_run(const orc_klgraph *g, uint8_t *side,
                    const int32_t *order0, int64_t n0, const int32_t *order1, int64_t n1,
                    float *cut, float *gain, int32_t *node1, int32_t *node2, int64_t capacity);
+/* the same pass with the literal O(|remain|) selection scans of cKL.cpp:341-355 (orc_kl_run caches the first
+ * best element per block of 256 positions so that 2 M-node passes finish in seconds; results are identical) */
+int64_t orc_kl_run_linear(const orc_klgraph *g, uint8_t *side,
+                          const int32_t *order0, int64_t n0, const int32_t *order1, int64_t n1,
+                          float *cut, float *gain, int32_t *node1, int32_t *node2, int64_t capacity);
 
 /* ---- EIG (cEIG.cpp:86-133, 194-220) -------------------------------------------------------- */
 typedef struct {

@@ -13,7 +13,7 @@ DEPS = SRCS + [os.path.join(CSRC, h) for h in ("internal.h", "stl_order.h")]
 def build():
     if os.path.exists(OUT) and all(os.path.getmtime(d) <= os.path.getmtime(OUT) for d in DEPS):
         return OUT
-    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-I" + CSRC,
+    subprocess.check_call(["/usr/bin/g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-pthread", "-I" + CSRC,
                            "-I" + os.path.join(ROOT, "include"), "-I/usr/local/cuda/include"] + SRCS +
                           ["-o", OUT, "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath,/usr/local/cuda/lib64"])
     return OUT

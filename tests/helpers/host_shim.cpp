@@ -29,10 +29,26 @@ int shim_write_eig(const char *path, double lambda2, double median, const double
 int shim_read_eig(const char *path, int32_t n, uint8_t *side, char *err, int errlen) {
   try {
     std::vector<uint8_t> s;
-    read_eig_file(path, n, s);
+    std::vector<int32_t> o0, o1;
+    bool asc = true;
+    read_eig_file(path, n, s, o0, o1, asc);
     std::copy(s.begin(), s.end(), side);
     return 0;
   } catch (const Error &e) { snprintf(err, errlen, "%s", e.what()); return e.code; }
+}
+// as above, plus remain[0] ++ remain[1] in file order (order must hold n ints); returns 1 when the file is ascending, 0 when not
+int shim_read_eig_orders(const char *path, int32_t n, uint8_t *side, int32_t *order, int32_t *n0) {
+  try {
+    std::vector<uint8_t> s;
+    std::vector<int32_t> o0, o1;
+    bool asc = true;
+    read_eig_file(path, n, s, o0, o1, asc);
+    std::copy(s.begin(), s.end(), side);
+    std::copy(o0.begin(), o0.end(), order);
+    std::copy(o1.begin(), o1.end(), order + o0.size());
+    *n0 = (int32_t)o0.size();
+    return asc ? 1 : 0;
+  } catch (const Error &e) { return e.code; }
 }
 int shim_sym_eig(int n, double *a, double *evals) {
   try { sym_eig(n, a, evals); return 0; } catch (const Error &e) { return e.code; }

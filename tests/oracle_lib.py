@@ -61,6 +61,8 @@ def lib():
         L.orc_kl_run.argtypes = [P(KlGraph), P(C.c_uint8), P(C.c_int32), C.c_int64, P(C.c_int32), C.c_int64,
                                  P(C.c_float), P(C.c_float), P(C.c_int32), P(C.c_int32), C.c_int64]
         L.orc_kl_run.restype = C.c_int64
+        L.orc_kl_run_linear.argtypes = L.orc_kl_run.argtypes
+        L.orc_kl_run_linear.restype = C.c_int64
         L.orc_laplacian.argtypes = [P(Hgr), P(Csr)]
         L.orc_csr_free.argtypes = [P(Csr)]
         L.orc_spmv.argtypes = [P(Csr), P(C.c_double), P(C.c_double)]
@@ -140,7 +142,9 @@ class OracleKL:
         return np.float32(lib().orc_kl_cut0(C.byref(self.g), _p(side, C.c_uint8), _p(o0, C.c_int32), len(o0),
                                             _p(o1, C.c_int32), len(o1)))
 
-    def run(self, side, order0=None, order1=None):
+    def run(self, side, order0=None, order1=None, linear=False):
+        """One KL pass.  linear=True: the literal O(|remain|) selection scans of cKL.cpp:341-355 instead of the
+        block-cached selection (identical results; only feasible up to ~100 K nodes)."""
         side = np.array(side, dtype=np.uint8, copy=True)
         o0, o1 = self._orders(side, order0, order1)
         cap = min(len(o0), len(o1)) + 1
@@ -148,7 +152,8 @@ class OracleKL:
         gain = np.zeros(cap, np.float32)
         n1 = np.zeros(cap, np.int32)
         n2 = np.zeros(cap, np.int32)
-        swaps = lib().orc_kl_run(C.byref(self.g), _p(side, C.c_uint8), _p(o0, C.c_int32), len(o0),
+        fn = lib().orc_kl_run_linear if linear else lib().orc_kl_run
+        swaps = fn(C.byref(self.g), _p(side, C.c_uint8), _p(o0, C.c_int32), len(o0),
                                  _p(o1, C.c_int32), len(o1), _p(cut, C.c_float), _p(gain, C.c_float),
                                  _p(n1, C.c_int32), _p(n2, C.c_int32), cap)
         s = int(swaps) + 1

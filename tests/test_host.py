@@ -18,6 +18,7 @@ def shim():
     L.shim_parse_hgr.argtypes = [C.c_char_p, P(C.c_int32), P(C.c_int32), P(C.c_int64), C.c_int64, P(C.c_int32), C.c_int64, C.c_char_p, C.c_int]
     L.shim_write_eig.argtypes = [C.c_char_p, C.c_double, C.c_double, P(C.c_double), C.c_int32]
     L.shim_read_eig.argtypes = [C.c_char_p, C.c_int32, P(C.c_uint8), C.c_char_p, C.c_int]
+    L.shim_read_eig_orders.argtypes = [C.c_char_p, C.c_int32, P(C.c_uint8), P(C.c_int32), P(C.c_int32)]
     L.shim_sym_eig.argtypes = [C.c_int, P(C.c_double), P(C.c_double)]
     L.shim_tridiag_top.argtypes = [C.c_int, P(C.c_double), P(C.c_double), C.c_int, P(C.c_double), P(C.c_double)]
     return L
@@ -77,6 +78,52 @@ def test_eig_writer_reproduces_golden_file(c, shim, oracle, workdir, tmp_path):
     err = C.create_string_buffer(256)
     assert shim.shim_read_eig(out.encode(), n, _p(side, C.c_uint8), err, 256) == 0
     assert np.array_equal(side, g["side"])
+
+
+def test_parallel_text_io_is_thread_count_independent(shim, oracle, circuits, workdir, tmp_path, monkeypatch):
+    # the parser / EIG writer / EIG reader split their input at newlines, one piece per thread: any thread count
+    # must give the same arrays and the same bytes (EIGKL_IO_THREADS overrides the automatic choice)
+    c = "ibm01"
+    h = oracle.OracleHgr(circuits[c])
+    gpath = datasets.golden_eig_path(workdir, c)
+    g = oracle.read_eig(gpath, h.n_nodes)
+    for threads in ("1", "2", "7", "16"):
+        monkeypatch.setenv("EIGKL_IO_THREADS", threads)
+        rc, nn, ne, off, pins, _ = _parse(shim, circuits[c])
+        assert rc == 0 and (nn, ne) == (h.n_nodes, h.n_nets)
+        assert np.array_equal(off[: ne + 1], h.net_off) and np.array_equal(pins[: off[ne]], h.pins)
+        out = str(tmp_path / f"o{threads}.txt")
+        assert shim.shim_write_eig(out.encode(), g["lambda2"], g["median"], _p(g["vec"], C.c_double), h.n_nodes) == 0
+        assert open(out, "rb").read() == open(gpath, "rb").read()
+        side = np.zeros(h.n_nodes, np.uint8)
+        order = np.zeros(h.n_nodes, np.int32)
+        n0 = C.c_int32()
+        assert shim.shim_read_eig_orders(out.encode(), h.n_nodes, _p(side, C.c_uint8), _p(order, C.c_int32), C.byref(n0)) == 1
+        assert np.array_equal(side, g["side"]) and n0.value == int((g["side"] == 0).sum())
+        assert np.array_equal(order[: n0.value], np.nonzero(g["side"] == 0)[0])
+    # a ragged file: no trailing newline, CRLF, blank lines, lines beyond <nets>, a non-numeric token ending a net
+    p = tmp_path / "r.hgr"
+    p.write_text("4 9\r\n1 2 3\r\n\r\n4 x 5\n6 7\n8 9\n1 2")
+    for threads in ("1", "3", "5"):
+        monkeypatch.setenv("EIGKL_IO_THREADS", threads)
+        rc, nn, ne, off, pins, _ = _parse(shim, str(p))
+        assert rc == 0 and (nn, ne) == (9, 4)
+        assert list(off[:5]) == [0, 3, 3, 4, 6] and list(pins[:6]) == [0, 1, 2, 3, 5, 6]
+
+
+def test_eig_reader_keeps_file_order_of_unsorted_files(shim, tmp_path, monkeypatch):
+    # cKL.cpp:166-173 appends nodes to remain[side] in FILE order; a file that is not ascending keeps that order
+    p = tmp_path / "u.txt"
+    p.write_text("0.1\n0.0\n3\t1\t0.5\n0\t0\t-0.5\n2\t1\t0\n1\t0\t0.25\n4\t0\t0.1\n")
+    for threads in ("1", "3"):
+        monkeypatch.setenv("EIGKL_IO_THREADS", threads)
+        side = np.zeros(5, np.uint8)
+        order = np.zeros(5, np.int32)
+        n0 = C.c_int32()
+        assert shim.shim_read_eig_orders(str(p).encode(), 5, _p(side, C.c_uint8), _p(order, C.c_int32), C.byref(n0)) == 0
+        assert list(side) == [0, 0, 1, 1, 0] and n0.value == 3 and list(order) == [0, 1, 4, 3, 2]
+    p.write_text("0.1\n0.0\n0\t1\t0.5\n0\t0\t-0.5\n1\t1\t0\n")       # node 0 twice
+    assert shim.shim_read_eig_orders(str(p).encode(), 2, _p(side, C.c_uint8), _p(order, C.c_int32), C.byref(n0)) == -3
 
 
 def test_eig_reader_errors(shim, tmp_path):
@@ -173,7 +220,7 @@ def test_cabi_exports_every_declared_symbol(eigkl_lib):
     assert declared == sorted(api.SYMBOLS)
     for s in declared:
         assert hasattr(eigkl_lib, s), s
-    assert eigkl_lib.eigkl_abi_version() == 1
+    assert eigkl_lib.eigkl_abi_version() == 2
 
 
 def test_ctypes_struct_layout_matches_header(tmp_path):

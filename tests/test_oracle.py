@@ -55,6 +55,29 @@ def test_oracle_kl_trace_byte_exact(c, oracle, workdir, circuits, tmp_path):
     assert int(r["side"].sum()) == int(g["side"].sum())
 
 
+@pytest.mark.parametrize("c", ["fract", "ibm01", "industry2"])
+def test_oracle_block_cached_selection_equals_linear_scan(c, oracle, workdir, circuits):
+    # orc_kl_run caches the first best element per 256 positions of remain[]; the literal scans of
+    # cKL.cpp:341-355 (orc_kl_run_linear) must give the same pass, from the golden start and from shuffled orders
+    h = oracle.OracleHgr(circuits[c])
+    kl = oracle.OracleKL(h)
+    g = oracle.read_eig(datasets.golden_eig_path(workdir, c), h.n_nodes)
+    rng = np.random.default_rng(7)
+    perm = rng.permutation(h.n_nodes).astype(np.int32)
+    half = h.n_nodes // 2
+    starts = [(g["side"], None, None)]
+    side = np.zeros(h.n_nodes, np.uint8)
+    side[perm[half:]] = 1
+    starts.append((side, perm[:half], perm[half:]))
+    for sd, o0, o1 in starts:
+        ra, rb = kl.run(sd, o0, o1), kl.run(sd, o0, o1, linear=True)
+        assert ra["swaps"] == rb["swaps"]
+        for k in ("node1", "node2", "side"):
+            assert np.array_equal(ra[k], rb[k])
+        for k in ("cut", "gain"):
+            assert np.array_equal(ra[k].view(np.uint32), rb[k].view(np.uint32))
+
+
 def test_oracle_kl_label_swap_invariance(oracle, workdir, circuits):
     # flipping every side bit leaves the gain column and the swap pairs unchanged
     c = "ibm01"
