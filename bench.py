@@ -10,7 +10,15 @@ segmented reduce) -> Fiedler solve (fp64 Lanczos) -> median split -> KL graph as
 HOST buffers (pinned): H2D of the pins and D2H of the Fiedler vector, sides and KL trace every step.
 Metric and workload follow BASELINE.json ("Fiedler solve ms & KL passes/sec on ibm18 ..."): ibm18.hgr
 is a missing blob of the reference, so the largest shipped real circuit,
-ibm10, stands in unless tests/data/circuit/ibm18.hgr(.gz) is present.
+ibm10, stands in unless tests/data/circuit/ibm18.hgr(.gz) is present.  The same line carries, under
+`workloads`, the two synthetic sizes BASELINE.json names -- circuit_generator scale 1 (ibm18-sized,
+201 920 nodes) and scale 10 (2 019 200 nodes) -- each with its stage times, per-kernel rooflines, e2e
+and CPU baseline, measured with fewer steps so that the default run stays within a few minutes.
+
+N > 1 (one process per GPU): ONE problem.  A circuit whose matrix fits one chip is solved replicated on
+every rank; a larger one runs the Lanczos solve row-partitioned (packed halos pushed over NVLink from
+the SpMV epilogue, NCCL all-reduces for the dot products); the KL pass is replicated.  Rank 0 re-runs
+the pass on a single-GPU handle and compares: `parity` in the line, non-zero exit on a mismatch.
 
 Prints ONE JSON line (rank 0).
 """
@@ -114,6 +122,15 @@ def host_threads():
         return os.cpu_count() or 1
 
 
+def pin_host_threads():
+    """torch.distributed.run exports OMP_NUM_THREADS=1 to its workers; the CPU legs must use the box's cores
+    whatever launched them (round 1's N>1 reference lines were 19x slower for this reason alone)."""
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_PROC_BIND", None)
+    return n
+
+
 # --------------------------------------------------------------------------------------------------
 # CPU legs (the only places that may touch oracle/)
 # --------------------------------------------------------------------------------------------------
@@ -138,6 +155,34 @@ def cpu_port_pass(path, golden_side=None, max_restarts=0):
                 matvecs=st["matvecs"], converged=st["converged"], swaps=r["swaps"], lambda2=lam)
 
 
+def cpu_baseline_for(name, path, gpu_matvecs, gpu_side=None):
+    """cpu_baseline of one workload, rank 0 at N = 1.  Real circuits: one full pass of the oracle port.
+    Synthetic circuits are disconnected (lambda2 = 0 with a 16 K-dimensional null space): the port's plain
+    restarted Lanczos does not converge on them within minutes, so its Fiedler stage is a BOUNDED sample -- a few
+    restart cycles timed, scaled to the number of matvecs the GPU solve needed (generous to the CPU: plain Lanczos
+    needs more steps than the filtered solve) -- and the KL pass runs in full from the GPU's partition."""
+    cores = pin_host_threads()
+    if not name.startswith("synth"):
+        p = cpu_port_pass(path)
+        sec = sum(p[k] for k in ("parse", "assemble_l", "fiedler", "assemble_kl", "kl"))
+        return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": f"one full pass of {name} by the oracle port (OpenMP C restatement of cEIG+cKL): "
+                          f"{p['matvecs']} Lanczos matvecs, {p['swaps']} KL swaps",
+                "seconds": {k: round(v, 4) for k, v in p.items() if isinstance(v, float) and k != "lambda2"}}
+    restarts = 3 if name in ("synth1", "synth") else 1
+    p = cpu_port_pass(path, golden_side=gpu_side, max_restarts=restarts)
+    per_mv = p["fiedler"] / max(1, p["matvecs"])
+    fied = per_mv * gpu_matvecs
+    sec = p["parse"] + p["assemble_l"] + fied + p["assemble_kl"] + p["kl"]
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{name}: parse, both assemblies and the full KL pass ({p['swaps']} swaps, from the GPU's partition) timed in full; "
+                      f"Fiedler stage = {p['matvecs']} Lanczos steps of the port timed ({p['fiedler']:.2f} s, full re-orthogonalisation, "
+                      f"ncv 100) and scaled to the {gpu_matvecs} matvecs of the GPU solve (the graph is disconnected: the port's "
+                      f"unfiltered Lanczos does not converge on the degenerate lambda2 = 0 within minutes)",
+            "seconds": {"parse": round(p["parse"], 4), "assemble_l": round(p["assemble_l"], 4), "fiedler_scaled": round(fied, 4),
+                        "fiedler_sampled": round(p["fiedler"], 4), "assemble_kl": round(p["assemble_kl"], 4), "kl": round(p["kl"], 4)}}
+
+
 def run_reference_arm(args, rank, world):
     """--impl reference: the reference's own CPU implementation on the host cores.
     KL = the UNMODIFIED reference program oracle/_ref/cKL (built from /root/reference/cKL.cpp by
@@ -145,11 +190,11 @@ def run_reference_arm(args, rank, world):
     Each step is a full pass of the workload; the number of steps is bounded by a time budget."""
     if rank != 0:
         return
+    cores = pin_host_threads()
     name = pick_workload(args.workload)
     wd = tempfile.mkdtemp(prefix="eigkl_ref_")
     path, has_golden = materialize_workload(name, wd)
     ckl = os.path.join(ROOT, "oracle", "_ref", "cKL")
-    cores = host_threads()
     budget = float(os.environ.get("EIGKL_REF_BUDGET_S", "200"))
     use_ref_kl = os.path.exists(ckl) and has_golden
     times = []
@@ -157,14 +202,14 @@ def run_reference_arm(args, rank, world):
     t_begin = time.perf_counter()
     steps_done = 0
     warm = 0
+    env = dict(os.environ, OMP_NUM_THREADS=str(cores))
     while steps_done < max(1, args.steps):
-        t0 = time.perf_counter()
         p = cpu_port_pass(path)                           # EIG (port) + KL (port, used only if no reference binary)
         t_eig = p["parse"] + p["assemble_l"] + p["fiedler"]
         if use_ref_kl:
             t1 = time.perf_counter()
             r = subprocess.run([ckl, os.path.join("circuit", name + ".hgr"), "-EIG"], cwd=wd, stdout=subprocess.PIPE,
-                               stderr=subprocess.PIPE, text=True)
+                               stderr=subprocess.PIPE, text=True, env=env)
             t_kl = time.perf_counter() - t1
             if r.returncode != 0:
                 use_ref_kl = False
@@ -188,7 +233,8 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": len(times),
             "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64 (Lanczos) + f32 (KL)", "data": "real circuit " + name + ".hgr" if not name.startswith("synth") else "synthetic",
-            "config": {"workload": name, "requested_steps": args.steps, "requested_warmup": args.warmup, "time_budget_s": budget},
+            "config": {"workload": name, "requested_steps": args.steps, "requested_warmup": args.warmup, "time_budget_s": budget,
+                       "host_threads": cores},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, **detail},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -198,43 +244,34 @@ def run_reference_arm(args, rank, world):
 # --------------------------------------------------------------------------------------------------
 # GPU arm
 # --------------------------------------------------------------------------------------------------
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="auto", help="auto | fract | ibm01 | industry2 | ibm10 | ibm18 | synth<scale>")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kl-cluster", type=int, default=0)
-    ap.add_argument("--keep", type=int, default=0)
-    args = ap.parse_args()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    if args.impl == "reference":
-        run_reference_arm(args, rank, world)
-        return
-    args.warmup = max(args.warmup, 3)
+class Ctx:
+    pass
 
+
+def load_peaks():
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"
+    return peak, src
+
+
+def measure(cx, name, steps, warmup, primary):
+    """All numbers of one workload.  Collective over the ranks; the returned dict is complete on rank 0."""
+    import ctypes as C
     import numpy as np
-    import torch
-    import torch.distributed as dist
-    from eig_kl_algorithm_b200 import api, build as _build, datasets
-
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the EIG+KL path has no CPU fallback (use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    _build.build()
-    name = pick_workload(args.workload)
-    wd = tempfile.mkdtemp(prefix="eigkl_bench_%d_" % rank)
-    path, _ = materialize_workload(name, wd)
+    torch, dist, api, datasets = cx.torch, cx.dist, cx.api, cx.datasets
+    rank, world, local_rank = cx.rank, cx.world, cx.local_rank
+    # ---- input: rank 0 materialises the file, every rank reads it ----
+    path = os.path.join(cx.shared, "circuit", name + ".hgr")
+    if rank == 0:
+        path, _ = materialize_workload(name, cx.shared)
+    cx.barrier()
     n_nodes, net_off, pins = datasets.read_hgr_arrays(path)
     n_nets = len(net_off) - 1
-    # pinned host buffers: inputs and the results a caller reads back
     t_off = torch.from_numpy(net_off).pin_memory()
     t_pins = torch.from_numpy(pins).pin_memory()
     cap = n_nodes // 2 + 2
@@ -245,13 +282,7 @@ def main():
     t_n1 = torch.empty(cap, dtype=torch.int32).pin_memory()
     t_n2 = torch.empty(cap, dtype=torch.int32).pin_memory()
 
-    import ctypes as C
-    nccl_id = None
-    if world > 1:
-        ids = [api.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        nccl_id = ids[0]
-    h = api.Handle(device=local_rank, rank=rank, nranks=world, nccl_id=nccl_id, kl_cluster=args.kl_cluster, keep=args.keep)
+    h = api.Handle(device=local_rank, rank=rank, nranks=world, nccl_id=cx.nccl_id(), kl_cluster=cx.args.kl_cluster, keep=cx.args.keep)
     lib = h.lib
     stream = torch.cuda.ExternalStream(h.stream_ptr(), device=torch.device("cuda", local_rank))
 
@@ -280,19 +311,14 @@ def main():
         h._check(lib.eigkl_kl_run(h._h, C.byref(trace)))                               # D2H: trace
         return lam.value, int(trace.swaps)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     def timed(fn, k):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        barrier()
+        cx.barrier()
         ev0.record(stream)
         for _ in range(k):
             fn()
         ev1.record(stream)
-        barrier()
+        cx.barrier()
         ms = ev0.elapsed_time(ev1)
         if world > 1:
             t = torch.tensor([ms], device="cuda")
@@ -301,146 +327,350 @@ def main():
         return ms
 
     upload()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step_resident()
     l0 = h.stats()["gpu_launches"]
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    ms_total = timed(step_resident, args.steps)
+    sampler = ClockSampler(local_rank) if primary else None
+    if sampler:
+        sampler.start()
+    ms_total = timed(step_resident, steps)
     launches = h.stats()["gpu_launches"] - l0
     st = h.stats()
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         lam, swaps = step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
-    clocks = sampler.stop()
-    st_e2e = h.stats()
+    ms_e2e = timed(step_e2e, steps)
+    clocks = sampler.stop() if sampler else None
     h2d = int(net_off.nbytes + pins.nbytes)
     d2h = int(n_nodes * 8 + n_nodes + (swaps + 1) * 16 + 8 * 4)
+    # results of the last e2e pass, for the parity check and the CPU baseline
+    vec_multi = t_vec.numpy().copy()
+    side_multi = t_side.numpy().copy()
+    tr_multi = dict(swaps=swaps, cut=t_cut.numpy()[:swaps + 1].copy(), gain=t_gain.numpy()[:swaps + 1].copy(),
+                    node1=t_n1.numpy()[:swaps + 1].copy(), node2=t_n2.numpy()[:swaps + 1].copy())
+    lam_multi = lam
 
-    # N>1: ONE problem, row-partitioned Lanczos over the N ranks (strong scaling); the O(ms) assembly and
-    # the latency-bound KL pass are replicated on every rank (multi-GPU)
-    passes = args.steps
-    value = passes / (ms_total * 1e-3)
-    e2e_value = passes / (ms_e2e * 1e-3)
+    # ---- per-kernel attribution: one extra profiled pass on the SAME handle (events around every launch), on every
+    # rank, so that the classes reported are the kernels that ran in the timed region (multi-rank path included)
+    peak, peak_src = cx.peak, cx.peak_src
+    h.set_profile(True)
+    step_resident()
+    s0 = h.stats()
+    step_resident()
+    s1 = h.stats()
+    h.set_profile(False)
+    kernels, roof = {}, None
+    spmv_iso = spmv_cold = dval_iso = dval_cold = None
+    if s1["dist_ranks"] <= 1:                       # isolated launches of the single-GPU streaming kernels
+        spmv_iso = h.time_kernel("spmv", iters=50, flush_l2=False)
+        spmv_cold = h.time_kernel("spmv", iters=20, flush_l2=True)
+    dval_iso = h.time_kernel("dvalues", iters=50, flush_l2=False)
+    dval_cold = h.time_kernel("dvalues", iters=20, flush_l2=True)
 
-    # ---- per-kernel attribution: one extra profiled pass on the same data (events around every launch)
-    roof, kernels = None, {}
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "6650 GB/s (of fallback, B200_PROFILING.md)"
-    if rank == 0:
-        with api.Handle(device=local_rank, kl_cluster=args.kl_cluster, keep=args.keep, flags=api.EIGKL_F_PROFILE) as hp:
-            hp.set_pins_ptr(n_nodes, n_nets, t_off.data_ptr(), t_pins.data_ptr())
-            for _ in range(2):
-                hp.invalidate(); hp.assemble_laplacian(); hp.fiedler(want_vector=False); hp.partition_from_fiedler(want_side=False)
-                hp.assemble_kl_graph(); hp.kl_run(want_trace=False)
-            s0 = hp.stats()
-            hp.invalidate(); hp.assemble_laplacian(); hp.fiedler(want_vector=False); hp.partition_from_fiedler(want_side=False)
-            hp.assemble_kl_graph(); hp.kl_run(want_trace=False)
-            s1 = hp.stats()
-            spmv_iso = hp.time_kernel("spmv", iters=50, flush_l2=False)
-            spmv_cold = hp.time_kernel("spmv", iters=20, flush_l2=True)
-            dval_iso = hp.time_kernel("dvalues", iters=50, flush_l2=False)
-            dval_cold = hp.time_kernel("dvalues", iters=20, flush_l2=True)
+    def cls(nm, bytes_total=None, bytes_each=None):
+        ms = s1["ms_" + nm] - s0["ms_" + nm]
+        cnt = s1["n_" + nm] - s0["n_" + nm]
+        if cnt <= 0:
+            return None
+        b = bytes_each * cnt if bytes_each is not None else bytes_total
+        return {"launches": int(cnt), "ms_total": ms, "us_avg": 1e3 * ms / cnt, "alg_bytes_per_launch": b / cnt,
+                "achieved_gbs": b / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}
 
-        def cls(nm, bytes_total=None, bytes_each=None):
-            ms = s1["ms_" + nm] - s0["ms_" + nm]
-            cnt = s1["n_" + nm] - s0["n_" + nm]
-            if cnt <= 0:
-                return None
-            b = bytes_each * cnt if bytes_each is not None else bytes_total
-            return {"launches": int(cnt), "ms_total": ms, "us_avg": 1e3 * ms / cnt, "alg_bytes_per_launch": b / cnt,
-                    "achieved_gbs": b / (ms * 1e-3) / 1e9, "frac_of_hbm_peak": b / (ms * 1e-3) / 1e9 / peak}
-        kernels["spmv"] = cls("spmv", bytes_each=s1["bytes_spmv"])
-        spl = int(s1.get("spmv_per_launch", 1) or 1)
-        if kernels["spmv"] and spl > 1:
-            # resident filter: ONE cooperative launch carries `spl` SpMVs (the library counts SpMVs); report per LAUNCH
-            k = kernels["spmv"]
-            k["spmv_count"] = k["launches"]
-            k["launches"] = k["launches"] // spl
-            k["spmv_per_launch"] = spl
-            k["resident_k"] = int(s1.get("resident_k", 0))
-            k["us_per_spmv"] = k["us_avg"]
-            k["us_avg"] = k["us_avg"] * spl
-            k["alg_bytes_per_launch"] = k["alg_bytes_per_launch"] * spl
-        kernels["multidot"] = cls("multidot", bytes_total=s1["bytes_multidot_total"] - s0["bytes_multidot_total"])
-        kernels["update"] = cls("update", bytes_total=s1["bytes_update_total"] - s0["bytes_update_total"])
-        kernels["restart"] = cls("restart", bytes_total=(s1["n_restart"] - s0["n_restart"]) * (s1["ncv"] + max(3, s1["ncv"] // 5)) * n_nodes * 8.0)
-        kernels["dvalues"] = cls("dvalues", bytes_each=s1["bytes_dvalues"])
-        kernels["kl_loop"] = {"launches": 1, "ms_total": s1["ms_kl_loop"], "swaps": s1["kl_swaps"],
-                              "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]),
-                              "state": {0: "global memory (cluster kernel)", 1: "tile keys + side bits in shared memory",
-                                        2: "tile keys in shared memory, state bytes in global memory"}.get(int(s1.get("kl_local", 0)), "?"),
-                              "bound": "latency (a chain of dependent L2 round trips per swap), not bandwidth"}
-        if kernels.get("multidot") and s1.get("gs_fused", 0):
-            kernels["multidot"]["note"] = ("fused Gram-Schmidt: ONE cooperative launch per Lanczos step does both passes "
-                                           "(h1, update, h2, update, DGKS decision, norm); %d basis columns cached in shared memory; "
-                                           "algorithmic bytes = the basis once + w in and out" % int(s1.get("gs_cache_cols", 0)))
+    kernels["spmv"] = cls("spmv", bytes_each=s1["bytes_spmv"])
+    spl = int(s1.get("spmv_per_launch", 1) or 1)
+    if kernels["spmv"] and spl > 1:
+        # resident filter: ONE cooperative launch carries `spl` SpMVs (the library counts SpMVs); report per LAUNCH
+        k = kernels["spmv"]
+        k["spmv_count"] = k["launches"]
+        k["launches"] = k["launches"] // spl
+        k["spmv_per_launch"] = spl
+        k["resident_k"] = int(s1.get("resident_k", 0))
+        k["us_per_spmv"] = k["us_avg"]
+        k["us_avg"] = k["us_avg"] * spl
+        k["alg_bytes_per_launch"] = k["alg_bytes_per_launch"] * spl
+        k["kernel"] = "cheb_resident_kernel (matrix in registers, x in shared memory, LL halo exchange through L2)"
+        k["bound"] = "on-chip / latency: shared-memory gathers + SM-to-SM halo hand-off; the HBM fraction is a secondary figure"
+    elif kernels["spmv"]:
+        kernels["spmv"]["kernel"] = "spmv_dist_kernel (row-partitioned, halo push fused)" if s1["dist_ranks"] > 1 else "spmv_flat_kernel"
+        kernels["spmv"]["bound"] = "hbm"
+    rows_here = s1["dist_rows"] if s1["dist_ranks"] > 1 else n_nodes
+    kernels["multidot"] = cls("multidot", bytes_total=s1["bytes_multidot_total"] - s0["bytes_multidot_total"])
+    kernels["update"] = cls("update", bytes_total=s1["bytes_update_total"] - s0["bytes_update_total"])
+    kernels["restart"] = cls("restart", bytes_total=(s1["n_restart"] - s0["n_restart"]) * (s1["ncv"] + max(3, s1["ncv"] // 5)) * rows_here * 8.0)
+    kernels["dvalues"] = cls("dvalues", bytes_each=s1["bytes_dvalues"])
+    kernels["kl_loop"] = {"launches": 1, "ms_total": s1["ms_kl_loop"], "swaps": s1["kl_swaps"],
+                          "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]),
+                          "state": {0: "global memory (cluster kernel)", 1: "tile keys + side bits in shared memory",
+                                    2: "tile keys in shared memory, state bytes in global memory"}.get(int(s1.get("kl_local", 0)), "?"),
+                          "bound": "latency (a chain of dependent L2 round trips per swap), not bandwidth"}
+    if kernels.get("multidot") and s1.get("gs_fused", 0):
+        kernels["multidot"]["note"] = ("fused Gram-Schmidt: ONE cooperative launch per Lanczos step does both passes "
+                                       "(h1, update, h2, update, DGKS decision, norm); %d basis columns cached in shared memory; "
+                                       "algorithmic bytes = the basis once + w in and out" % int(s1.get("gs_cache_cols", 0)))
+    if s1["dist_ranks"] > 1:
+        ncm, nps = s1["n_comm"] - s0["n_comm"], s1["n_push"] - s0["n_push"]
+        kernels["exchange"] = {
+            "halo_values_received_per_spmv": int(s1["dist_halo"]), "rows_pushed_per_spmv": int(s1["dist_exports"]),
+            "rows_of_this_rank": int(s1["dist_rows"]),
+            "nccl_allreduce": {"calls": int(ncm), "us_avg": 1e3 * (s1["ms_comm"] - s0["ms_comm"]) / max(1, ncm),
+                               "ms_total": s1["ms_comm"] - s0["ms_comm"]},
+            "standalone_halo_push": {"launches": int(nps), "us_avg": 1e3 * (s1["ms_push"] - s0["ms_push"]) / max(1, nps)},
+            "note": "rank 0's view; every SpMV but the first of a filter application pushes its export rows from its own epilogue "
+                    "(inside the spmv class above); the Lanczos dot products / norms are ncclAllReduce calls"}
+    if spmv_iso is not None:
         kernels["spmv_isolated"] = {"us_avg_l2_warm": spmv_iso * 1e3, "us_avg_l2_flushed": spmv_cold * 1e3,
                                     "gbs_l2_warm": s1["bytes_spmv"] / (spmv_iso * 1e-3) / 1e9,
                                     "gbs_l2_flushed": s1["bytes_spmv"] / (spmv_cold * 1e-3) / 1e9}
-        kernels["dvalues_isolated"] = {"us_avg_l2_warm": dval_iso * 1e3, "us_avg_l2_flushed": dval_cold * 1e3,
-                                       "gbs_l2_warm": s1["bytes_dvalues"] / (dval_iso * 1e-3) / 1e9,
-                                       "gbs_l2_flushed": s1["bytes_dvalues"] / (dval_cold * 1e-3) / 1e9}
-        stream_classes = {k: v for k, v in kernels.items() if v and k in ("spmv", "multidot", "update", "restart", "dvalues")}
-        dom = max(stream_classes, key=lambda k: stream_classes[k]["ms_total"])
-        traffic = None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-            traffic = tj.get(name, {}).get(dom + "_resident" if dom == "spmv" and spl > 1 else dom)
-        except Exception:
-            pass
-        d = stream_classes[dom]
-        roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                "frac": d["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
-                "us_avg": d["us_avg"], "launches_in_pass": d["launches"],
-                "note": "average over every launch of this kernel in one extra profiled pass on the same resident data (CUDA events on the "
-                        "library's stream). spmv: one launch of the resident filter kernel carries spmv_per_launch SpMVs (a whole Chebyshev "
-                        "filter application; matrix in registers, x in shared memory, halo through L2), so its algorithmic bytes are "
-                        "spmv_per_launch * (nnz*12 + n*20) while its DRAM traffic is one read of the matrix; when the matrix does not fit "
-                        "on chip each SpMV is its own launch. The circuit is L2-resident: the fraction compares algorithmic bytes/time with "
-                        "the HBM copy peak, it is not HBM utilisation (DESIGN.md section 4)"}
-        if dom == "spmv" and spl > 1:
-            roof["spmv_per_launch"] = spl
+    kernels["dvalues_isolated"] = {"us_avg_l2_warm": dval_iso * 1e3, "us_avg_l2_flushed": dval_cold * 1e3,
+                                   "gbs_l2_warm": s1["bytes_dvalues"] / (dval_iso * 1e-3) / 1e9,
+                                   "gbs_l2_flushed": s1["bytes_dvalues"] / (dval_cold * 1e-3) / 1e9,
+                                   "frac_of_hbm_peak_l2_flushed": s1["bytes_dvalues"] / (dval_cold * 1e-3) / 1e9 / peak}
+    stream_classes = {k: v for k, v in kernels.items() if v and k in ("spmv", "multidot", "update", "restart", "dvalues")}
+    dom = max(stream_classes, key=lambda k: stream_classes[k]["ms_total"])
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(name, {}).get(dom + "_resident" if dom == "spmv" and spl > 1 else dom)
+    except Exception:
+        pass
+    d = stream_classes[dom]
+    resident = dom == "spmv" and spl > 1
+    roof = {"kernel": dom, "bound": "hbm", "achieved": d["achieved_gbs"], "peak": peak, "unit": "GB/s",
+            "frac": d["achieved_gbs"] / peak, "traffic": traffic, "peak_source": peak_src,
+            "us_avg": d["us_avg"], "launches_in_pass": d["launches"],
+            "limited_by": ("on-chip / latency (matrix in registers, x in shared memory, halo hand-off between SMs through L2): the "
+                           "fraction compares ALGORITHMIC bytes per time with the HBM copy peak, it is not HBM utilisation"
+                           if resident else "hbm"),
+            "note": "average over every launch of this kernel class in one extra profiled pass on the same handle and data (CUDA "
+                    "events on the library's stream), rank 0. spmv: when the matrix fits on chip one launch of the resident filter "
+                    "kernel carries spmv_per_launch SpMVs (a whole Chebyshev filter application), so its algorithmic bytes are "
+                    "spmv_per_launch * (nnz*12 + n*20) while its DRAM traffic is one read of the matrix; otherwise each SpMV is "
+                    "its own launch and the bytes are those of this rank's rows (DESIGN.md section 4)"}
+    if resident:
+        roof["spmv_per_launch"] = spl
+
+    # ---- N > 1: the multi-rank results against a single-GPU pass of the same circuit (rank 0) ----
+    parity = None
+    if world > 1:
+        ok = True
+        if rank == 0:
+            with api.Handle(device=local_rank, kl_cluster=cx.args.kl_cluster, keep=cx.args.keep) as h1:
+                h1.set_pins(n_nodes, net_off, pins)
+                h1.assemble_laplacian()
+                lam1, v1 = h1.fiedler()
+                r1 = h1.stats()["resid_est"][1]
+                med1, side1 = h1.partition_from_fiedler()
+                h1.assemble_kl_graph()
+                tr1 = h1.kl_run()
+                h1.set_partition(side_multi)                   # the KL pass from the multi-rank partition, on one GPU
+                trs = h1.kl_run()
+
+            def same(a, b):
+                return bool(a["swaps"] == b["swaps"] and np.array_equal(a["node1"], b["node1"]) and np.array_equal(a["node2"], b["node2"])
+                            and np.array_equal(a["cut"].view(np.uint32), b["cut"].view(np.uint32))
+                            and np.array_equal(a["gain"].view(np.uint32), b["gain"].view(np.uint32)))
+            simple = abs(lam1) > 1e-9
+            cs = abs(float(vec_multi @ v1))
+            sine = float(np.sqrt(max(0.0, 1.0 - cs * cs)))
+            lam_err = abs(lam_multi - lam1) / abs(lam1) if simple else abs(lam_multi - lam1)
+            parity = {"lambda_rel" if simple else "lambda_abs": lam_err, "sine": sine if simple else None,
+                      "true_residual": st["resid_est"][1], "true_residual_1gpu": r1,
+                      "kl_trace_equal_from_same_partition": same(tr_multi, trs),
+                      "fused_trace_equal": same(tr_multi, tr1), "sides_equal": bool(np.array_equal(side_multi, side1)),
+                      "mode": "replicated" if st["dist_ranks"] <= 1 else "row-partitioned over %d ranks" % st["dist_ranks"]}
+            ok = lam_err < 1e-9 and parity["kl_trace_equal_from_same_partition"] and st["converged"] == 1
+            if simple:
+                ok = ok and sine < 1e-7 and parity["fused_trace_equal"]
+            else:
+                parity["note"] = ("lambda2 = 0 is degenerate on this disconnected graph: any null-space vector is a valid answer, so the "
+                                  "vectors (and the partitions cut from them) are compared by residual, not by sine; the KL pass is "
+                                  "compared from the same partition")
+            parity["ok"] = bool(ok)
+        cx.barrier()
+        flag = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        cx.parity_ok = cx.parity_ok and bool(flag.item())
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        p = cpu_port_pass(path)
-        sec = sum(p[k] for k in ("parse", "assemble_l", "fiedler", "assemble_kl", "kl"))
-        cpu = {"value": 1.0 / sec, "unit": UNIT, "cores": host_threads(), "kind": "port",
-               "sample": f"one full pass of {name} by the oracle port (OpenMP C restatement of cEIG+cKL): "
-                         f"{p['matvecs']} Lanczos matvecs, {p['swaps']} KL swaps",
-               "seconds": {k: round(v, 4) for k, v in p.items() if isinstance(v, float) and k != "lambda2"}}
+    if rank == 0 and world == 1 and not cx.args.no_cpu_baseline:
+        cpu = cpu_baseline_for(name, path, st["matvecs"], side_multi)
+
+    h.close()
+    del t_off, t_pins, t_vec, t_side, t_cut, t_gain, t_n1, t_n2
+    torch.cuda.empty_cache()
+    if st["dist_ranks"] > 1:
+        par = ("Lanczos row-partitioned over %d ranks: nnz-balanced row cuts, packed halos pushed over NVLink from the SpMV epilogue "
+               "(peer-mapped memory, flags), NCCL all-reduces for the dot products; assembly and the latency-bound KL pass replicated" % world)
+    elif world > 1:
+        par = "the matrix fits one chip: every one of the %d ranks solves the whole problem (replicas of ONE bipartition), no data-path collective" % world
+    else:
+        par = "1 GPU"
+    return {"workload": name, "value": steps / (ms_total * 1e-3), "unit": UNIT, "steps": steps, "warmup": warmup,
+            "ms_per_step": ms_total / steps,
+            "config": {"workload": name, "nodes": n_nodes, "nets": n_nets, "pins": int(len(pins)), "parallelism": par,
+                       "l2": ("working set < L2: every step re-assembles and re-solves from the resident pins; inputs are not flushed between steps"
+                              if n_nodes < 500000 else "working set (matrix 157 MB, basis 1.6 GB) > L2 (126 MB): inputs larger than L2, no flush needed"),
+                       "ncv": st["ncv"], "cheb_degree": st["cheb_degree"], "lanczos_steps": st["lanczos_steps"],
+                       "spmv_per_pass": st["matvecs"], "restarts": st["restarts"],
+                       "true_residual": st["resid_est"][1], "kl_swaps": st["kl_swaps"], "kl_cluster": st["kl_cluster"],
+                       "dist_ranks": st["dist_ranks"]},
+            "stage_ms": {"assemble_laplacian": st["ms_assemble_laplacian"], "fiedler_solve": st["ms_fiedler"],
+                         "partition": st["ms_partition"], "assemble_kl": st["ms_assemble_kl"], "kl_setup": st["ms_kl_setup"],
+                         "kl_loop": st["ms_kl_loop"]},
+            "fiedler_solve_ms": st["ms_fiedler"], "kl_pass_ms": st["ms_kl_setup"] + st["ms_kl_loop"],
+            "kl_swaps_per_s": st["kl_swaps"] / max(1e-9, st["ms_kl_loop"] * 1e-3),
+            "lambda2": lam_multi, "clocks": clocks,
+            "e2e": {"value": steps / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e / steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches), "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "parity": parity}
+
+
+def gpu_reference_leg(workdir):
+    """The reference's own GPU program (gKL.cu rebuilt for sm_100a by oracle/build_ref.sh) on the same box:
+    OMP_NUM_THREADS=1 (its threaded loader races), wall clock minus its hard-coded 3 s sleep (gKL.cu:702)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "gKL_sm100a")
+    if not os.path.exists(exe):
+        return {"unavailable": "oracle/_ref/gKL_sm100a not built"}
+    from eig_kl_algorithm_b200 import datasets
+    out = {}
+    datasets.materialize(workdir, circuits=("ibm01", "ibm10"), golden_eig=True)
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    for c in ("ibm01", "ibm10"):
+        t0 = time.perf_counter()
+        try:
+            r = subprocess.run([exe, os.path.join("circuit", c + ".hgr"), "-EIG"], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                               text=True, env=env, timeout=120)
+        except subprocess.TimeoutExpired:
+            out[c] = {"error": "timeout"}
+            continue
+        wall = time.perf_counter() - t0
+        it = [ln for ln in r.stdout.splitlines() if "iteration" in ln.lower()]
+        out[c] = {"rc": r.returncode, "wall_s": round(wall, 3), "wall_minus_sleep_s": round(wall - 3.0, 3), "last_iteration_line": it[-1].strip() if it else None}
+    out["how"] = "reference gKL.cu rebuilt -gencode arch=compute_100a,code=sm_100a; `gKL_sm100a circuit/<c>.hgr -EIG`; wall clock minus the 3 s sleep of gKL.cu:702"
+    return out
+
+
+def cli_e2e_leg(workdir):
+    """What a user of the drop-in waits for: wall clock of bin/cEIG + bin/cKL -EIG (CUDA context creation, text parse,
+    GPU work, file output), next to the reference's cKL binary on the same files."""
+    from eig_kl_algorithm_b200 import api, datasets
+    datasets.materialize(workdir, circuits=("ibm01", "ibm10"), golden_eig=True)
+    out = {}
+    ref = os.path.join(ROOT, "oracle", "_ref", "cKL")
+    env = dict(os.environ, OMP_NUM_THREADS=str(host_threads()))
+    for c in ("ibm01", "ibm10"):
+        rec = {}
+        for exe, argv in (("cEIG", [os.path.join("circuit", c + ".hgr")]), ("cKL", [os.path.join("circuit", c + ".hgr"), "-EIG"])):
+            t0 = time.perf_counter()
+            r = subprocess.run([os.path.join(api.BIN_DIR, exe)] + argv, cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+            rec[exe + "_wall_s"] = round(time.perf_counter() - t0, 4)
+            rec[exe + "_rc"] = r.returncode
+        if c == "ibm01" and os.path.exists(ref):            # ibm10 takes the reference ~25 s: that number is the reference arm's kl_s
+            datasets.materialize(workdir, circuits=(c,), golden_eig=True)      # the reference reads the golden EIG file
+            t0 = time.perf_counter()
+            r = subprocess.run([ref, os.path.join("circuit", c + ".hgr"), "-EIG"], cwd=workdir, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+            rec["reference_cKL_wall_s"] = round(time.perf_counter() - t0, 4)
+        out[c] = rec
+    out["how"] = ("wall clock of the drop-in executables, each a fresh process (CUDA context creation ~0.3 s included): `cEIG circuit/<c>.hgr` "
+                  "(parse, assembly, Lanczos, parallel %.12g writer) then `cKL circuit/<c>.hgr -EIG` (parse, EIG reader, assembly, KL pass, trace file)")
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="auto", help="auto | fract | ibm01 | industry2 | ibm10 | ibm18 | synth<scale>")
+    ap.add_argument("--extra", default="synth1,synth10", help="comma list of further workloads reported under `workloads` ('' = none)")
+    ap.add_argument("--extra-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-legs", action="store_true", help="skip the gpu_reference and cli_e2e legs")
+    ap.add_argument("--kl-cluster", type=int, default=0)
+    ap.add_argument("--keep", type=int, default=0)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    from eig_kl_algorithm_b200 import api, build as _build, datasets
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the EIG+KL path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    _build.build()
+
+    cx = Ctx()
+    cx.torch, cx.dist, cx.api, cx.datasets, cx.args = torch, dist, api, datasets, args
+    cx.rank, cx.world, cx.local_rank = rank, world, local_rank
+    cx.peak, cx.peak_src = load_peaks()
+    cx.parity_ok = True
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    cx.barrier = barrier
+
+    def nccl_id():
+        if world == 1:
+            return None
+        ids = [api.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        return ids[0]
+    cx.nccl_id = nccl_id
+    shared = [tempfile.mkdtemp(prefix="eigkl_bench_") if rank == 0 else None]
+    if world > 1:
+        dist.broadcast_object_list(shared, src=0)
+    cx.shared = shared[0]
+
+    name = pick_workload(args.workload)
+    main_res = measure(cx, name, args.steps, args.warmup, primary=True)
+    extras = {}
+    extra_names = [x for x in args.extra.split(",") if x and x != name] if args.workload == "auto" else []
+    for ex in extra_names:
+        extras[ex] = measure(cx, ex, max(1, args.extra_steps), 3, primary=False)
+
+    legs = {}
+    if rank == 0 and world == 1 and not args.no_legs:
+        wd = tempfile.mkdtemp(prefix="eigkl_legs_")
+        try:
+            legs["gpu_reference"] = gpu_reference_leg(wd)
+        except Exception as e:                                  # a leg never takes the line down
+            legs["gpu_reference"] = {"error": repr(e)}
+        try:
+            legs["cli_e2e"] = cli_e2e_leg(wd)
+        except Exception as e:
+            legs["cli_e2e"] = {"error": repr(e)}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-                "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        m = main_res
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": m["ms_per_step"], "higher_is_better": True,
                 "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64 (Lanczos) + f32 (KL, bit-exact with the reference)",
                 "data": ("real circuit %s.hgr (ISPD98)" % name) if not name.startswith("synth") else "synthetic (seeded circuit_generator restatement)",
-                "config": {"workload": name, "nodes": n_nodes, "nets": n_nets, "pins": int(len(pins)),
-                           "parallelism": ("Lanczos row-partitioned over %d ranks (NCCL halo all-gather + dot all-reduces); KL D-values/arg-max partitioned by node range with one NCCL max all-reduce per swap; O(1 ms) assembly replicated" % world) if world > 1 else "1 GPU",
-                           "l2": "working set < L2: every step re-assembles and re-solves from the resident pins; inputs are not flushed between steps",
-                           "ncv": st["ncv"], "cheb_degree": st["cheb_degree"], "lanczos_steps": st["lanczos_steps"],
-                           "spmv_per_pass": st["matvecs"], "restarts": st["restarts"],
-                           "true_residual": st["resid_est"][1], "kl_swaps": st["kl_swaps"], "kl_cluster": st["kl_cluster"]},
-                "stage_ms": {"assemble_laplacian": st["ms_assemble_laplacian"], "fiedler_solve": st["ms_fiedler"],
-                             "partition": st["ms_partition"], "assemble_kl": st["ms_assemble_kl"], "kl_setup": st["ms_kl_setup"],
-                             "kl_loop": st["ms_kl_loop"]},
-                "fiedler_solve_ms": st["ms_fiedler"], "kl_pass_ms": st["ms_kl_setup"] + st["ms_kl_loop"],
-                "kl_swaps_per_s": st["kl_swaps"] / max(1e-9, st["ms_kl_loop"] * 1e-3),
-                "lambda2": lam, "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                "gpu_launches": int(launches),
-                "roofline": roof, "kernels": kernels, "cpu_baseline": cpu}
+                "config": m["config"], "stage_ms": m["stage_ms"], "fiedler_solve_ms": m["fiedler_solve_ms"], "kl_pass_ms": m["kl_pass_ms"],
+                "kl_swaps_per_s": m["kl_swaps_per_s"], "lambda2": m["lambda2"], "clocks": m["clocks"], "e2e": m["e2e"],
+                "gpu_launches": m["gpu_launches"], "roofline": m["roofline"], "kernels": m["kernels"], "cpu_baseline": m["cpu_baseline"]}
+        if world > 1:
+            line["parity"] = m["parity"]
+        if extras:
+            line["workloads"] = {k: {kk: vv for kk, vv in v.items() if kk not in ("workload", "unit", "clocks")} for k, v in extras.items()}
+        line.update(legs)
         print(json.dumps(line), flush=True)
-    h.close()
     if world > 1:
         dist.destroy_process_group()
+    if not cx.parity_ok:
+        raise SystemExit("bench.py: multi-rank results differ from the single-GPU pass (see `parity`)")
 
 
 if __name__ == "__main__":

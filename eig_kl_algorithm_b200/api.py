@@ -27,7 +27,7 @@ SYMBOLS = [
     "eigkl_invalidate", "eigkl_get_stream", "eigkl_row_partition",
     "eigkl_assemble_laplacian", "eigkl_fiedler", "eigkl_partition_from_fiedler", "eigkl_write_eig",
     "eigkl_assemble_kl_graph", "eigkl_set_partition", "eigkl_set_partition_ordered", "eigkl_load_eig",
-    "eigkl_kl_run", "eigkl_write_trace", "eigkl_get_partition", "eigkl_spmv", "eigkl_dvalues", "eigkl_cut",
+    "eigkl_kl_run", "eigkl_write_trace", "eigkl_get_partition", "eigkl_kl_rollback", "eigkl_write_partition", "eigkl_spmv", "eigkl_dvalues", "eigkl_cut",
     "eigkl_get_kl_values", "eigkl_get_node_order",
     "eigkl_get_laplacian", "eigkl_get_kl_graph", "eigkl_time_kernel",
 ]
@@ -123,6 +123,8 @@ def load_library(path=LIB_PATH):
     L.eigkl_kl_run.argtypes = [H, P(Trace)]
     L.eigkl_write_trace.argtypes = [C.c_char_p, P(Trace)]
     L.eigkl_get_partition.argtypes = [H, P(C.c_uint8)]
+    L.eigkl_kl_rollback.argtypes = [H, P(C.c_int64), P(C.c_float)]
+    L.eigkl_write_partition.argtypes = [H, C.c_char_p]
     L.eigkl_spmv.argtypes = [H, P(C.c_double), P(C.c_double)]
     L.eigkl_dvalues.argtypes = [H, P(C.c_float)]
     L.eigkl_cut.argtypes = [H, P(C.c_float)]
@@ -282,6 +284,15 @@ class Handle:
         side = np.empty(self.n_nodes, np.uint8)
         self._check(self.lib.eigkl_get_partition(self._h, _ptr(side, C.c_uint8)))
         return side
+
+    def kl_rollback(self):
+        """Undo the swaps after the best prefix of the last pass; returns (kept row, its cut)."""
+        row, cut = C.c_int64(), C.c_float()
+        self._check(self.lib.eigkl_kl_rollback(self._h, C.byref(row), C.byref(cut)))
+        return row.value, np.float32(cut.value)
+
+    def write_partition(self, path):
+        self._check(self.lib.eigkl_write_partition(self._h, os.fsencode(path)))
 
     # ---- hooks ----------------------------------------------------------------------------------------
     def spmv(self, x):

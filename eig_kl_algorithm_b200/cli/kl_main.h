@@ -11,9 +11,28 @@
 
 // gkl_flavour: usage text on stderr when argc < 2 (gKL.cu:673-676); cKL prints it on stdout when
 // argc is not 2 or 3 (cKL.cpp:431-434).  Both return 1.
-inline int kl_main(int argc, char *argv[], bool gkl_flavour) {
+// Extensions (none of them changes what the reference's own argv forms do):
+//   --seed <n>             seed of the random initial partition (cKL.cpp:175-193 shuffles with an unseeded
+//                          mt19937; EIGKL_SEED in the environment does the same)
+//   --rollback             keep only the swaps up to the best cut (the reference tracks it, cKL.cpp:363, and stops there)
+//   --partition-out <file> write the final partition, "<node>\t<side>" per line (default name with --rollback alone:
+//                          results/<base>_KL_partition[_EIG].txt)
+inline int kl_main(int argc_all, char *argv_all[], bool gkl_flavour) {
   create_dir("results");                                              // cKL.cpp:428-429
   create_dir("pre_saved_EIG");
+  bool rollback = false, have_seed = false;
+  unsigned long seed_value = 0;
+  std::string partition_out;
+  std::vector<char *> pos;
+  for (int i = 0; i < argc_all; ++i) {
+    const std::string a = argv_all[i];
+    if (i > 0 && a == "--rollback") rollback = true;
+    else if (i > 0 && a == "--seed" && i + 1 < argc_all) { have_seed = true; seed_value = strtoul(argv_all[++i], nullptr, 10); }
+    else if (i > 0 && a == "--partition-out" && i + 1 < argc_all) partition_out = argv_all[++i];
+    else pos.push_back(argv_all[i]);
+  }
+  const int argc = (int)pos.size();
+  char **argv = pos.data();
   if (gkl_flavour ? (argc < 2) : (argc != 2 && argc != 3)) {
     (gkl_flavour ? std::cerr : std::cout) << "Usage: " << argv[0] << " <input_file> [-EIG]" << std::endl;
     return 1;
@@ -60,7 +79,8 @@ inline int kl_main(int argc, char *argv[], bool gkl_flavour) {
     std::vector<int32_t> ids((size_t)nodes);
     std::iota(ids.begin(), ids.end(), 0);
     const char *seed_env = getenv("EIGKL_SEED");
-    std::mt19937 gen(seed_env ? (unsigned)strtoul(seed_env, nullptr, 10) : std::random_device{}());
+    const unsigned seed = have_seed ? (unsigned)seed_value : seed_env ? (unsigned)strtoul(seed_env, nullptr, 10) : std::random_device{}();
+    std::mt19937 gen(seed);
     std::shuffle(ids.begin(), ids.end(), gen);
     n0 = nodes / 2; n1 = nodes - n0;
     if (eigkl_set_partition_ordered(h, ids.data(), n0, ids.data() + n0, n1) != EIGKL_OK) return fail(std::string("Error occurred: ") + eigkl_last_error(h));
@@ -80,6 +100,14 @@ inline int kl_main(int argc, char *argv[], bool gkl_flavour) {
   eigkl_get_stats(h, &st);
   float best = cut[0];
   for (int64_t i = 1; i <= tr.swaps; ++i) best = std::min(best, cut[(size_t)i]);
+  if (rollback || !partition_out.empty()) {
+    if (partition_out.empty()) partition_out = "results/" + base + (eig_init ? "_KL_partition_EIG.txt" : "_KL_partition.txt");
+    int64_t kept = tr.swaps;
+    float kept_cut = cut[(size_t)tr.swaps];
+    if (rollback && eigkl_kl_rollback(h, &kept, &kept_cut) != EIGKL_OK) return fail(std::string("Error occurred: ") + eigkl_last_error(h));
+    if (eigkl_write_partition(h, partition_out.c_str()) != EIGKL_OK) return fail("Error: Cannot open output file");
+    std::cout << "\nPartition written to " << partition_out << " (after swap " << kept << ", cut " << kept_cut << ")\n";
+  }
   std::cout << "\nInitial Partition Information:\n  - Left partition size: " << n0 << "\n  - Right partition size: " << n1
             << "\n  - Initial cut size: " << cut[0] << "\n";
   std::cout << "\n\n=============== Final Results =================\n";

@@ -401,6 +401,25 @@ int eigkl_get_partition(eigkl_handle *h, uint8_t *side) {
   });
 }
 
+int eigkl_kl_rollback(eigkl_handle *h, int64_t *best_row, float *best_cut) {
+  return guarded(h, [&] {
+    EIGKL_CUDA(cudaSetDevice(h->device));
+    const int64_t b = kl_rollback(h, best_cut);
+    if (best_row) *best_row = b;
+  });
+}
+
+int eigkl_write_partition(eigkl_handle *h, const char *path) {
+  return guarded(h, [&] {
+    EIGKL_REQUIRE(path && h->kl.have_partition, EIGKL_E_ARG, "eigkl_write_partition: no partition");
+    EIGKL_CUDA(cudaSetDevice(h->device));
+    std::vector<uint8_t> side((size_t)h->hg.n_nodes);
+    EIGKL_CUDA(cudaMemcpyAsync(side.data(), h->kl.state.p, side.size(), cudaMemcpyDeviceToHost, h->stream));
+    EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+    write_partition_file(path, side.data(), h->hg.n_nodes);
+  });
+}
+
 int eigkl_spmv(eigkl_handle *h, const double *x, double *y) {
   return guarded(h, [&] {
     EIGKL_REQUIRE(x && y && h->L.valid, EIGKL_E_ARG, "eigkl_spmv: Laplacian not assembled");

@@ -279,4 +279,26 @@ void write_trace_file(const char *path, const eigkl_trace *t) {
   if (fwrite(buf.data(), 1, buf.size(), f.get()) != buf.size()) throw Error(EIGKL_E_IO, std::string("short write: ") + path);
 }
 
+// "<node>\t<side>" per line, nodes ascending (0-based, like the EIG file): the partition the reference computes but
+// never writes (cKL.cpp:395-405)
+void write_partition_file(const char *path, const uint8_t *side, int32_t n) {
+  File f(fopen(path, "w"));
+  if (!f) throw Error(EIGKL_E_IO, std::string("Error: Cannot open output file: ") + path);
+  const int T = io_threads((size_t)n * 10);
+  std::vector<std::string> part((size_t)T);
+  run_parallel(T, [&](int t) {
+    const int32_t lo = (int32_t)((int64_t)n * t / T), hi = (int32_t)((int64_t)n * (t + 1) / T);
+    std::string &buf = part[(size_t)t];
+    buf.reserve((size_t)(hi - lo) * 12 + 16);
+    char tmp[32];
+    for (int32_t i = lo; i < hi; ++i) {
+      const int len = snprintf(tmp, sizeof(tmp), "%d\t%d\n", i, (int)(side[i] & 1u));
+      buf.append(tmp, (size_t)len);
+    }
+  });
+  for (int t = 0; t < T; ++t)
+    if (fwrite(part[(size_t)t].data(), 1, part[(size_t)t].size(), f.get()) != part[(size_t)t].size())
+      throw Error(EIGKL_E_IO, std::string("short write: ") + path);
+}
+
 }  // namespace eigkl

@@ -394,6 +394,7 @@ void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev);   // asc
 void kl_dvalues(eigkl_handle *h);                 // val[] for every node from the current sides
 float kl_cut0(eigkl_handle *h);
 void kl_run(eigkl_handle *h);
+int64_t kl_rollback(eigkl_handle *h, float *best_cut);
 
 // ---- text I/O (hgr_io.cpp) -----------------------------------------------------------------------------
 struct HostHgr {
@@ -406,6 +407,7 @@ void write_eig_file(const char *path, double lambda2, double median, const doubl
 void read_eig_file(const char *path, int32_t n, std::vector<uint8_t> &side, std::vector<int32_t> &order0,
                    std::vector<int32_t> &order1, bool &ascending);
 void write_trace_file(const char *path, const eigkl_trace *t);
+void write_partition_file(const char *path, const uint8_t *side, int32_t n);
 
 // ---- comm (comm.cpp) --------------------------------------------------------------------------------------
 void comm_init(eigkl_handle *h);

@@ -790,6 +790,7 @@ struct KlLocalParams {
   float cut0;
   uint32_t term_limit;
   int64_t n0, n1;
+  int clocks;
 };
 
 __global__ void nb_extent_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col, int64_t nnz, int2 *__restrict__ nb) {
@@ -837,13 +838,10 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
     tile_scan_local<ASC, GBITS>(bits, p.state, p.val, p.rank, p.n, t, lane, keys);
   __syncthreads();
   uint32_t it_local = 0;
-#ifdef EIGKL_KL_CLOCKS
+  // phase clocks of thread 0 (EIGKL_KL_PHASES=1): one predicated clock read per phase
   long long tph[6] = {0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
-#define KL_PHASE(i) do { if (tid == 0) { const long long t_ = clock64(); tph[i] += t_ - tprev; tprev = t_; } } while (0)
-#else
-#define KL_PHASE(i) do { } while (0)
-#endif
+#define KL_PHASE(i) do { if (p.clocks && tid == 0) { const long long t_ = clock64(); tph[i] += t_ - tprev; tprev = t_; } } while (0)
 
   while (!sh_done) {
     // ---- S1: best pair over the tile keys (shared memory) ----
@@ -982,11 +980,39 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
   }
   if (tid == 0) {
     p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1;
-#ifdef EIGKL_KL_CLOCKS
-    for (int i = 0; i < 6; ++i) p.ctrl[8 + i] = tph[i];
-#endif
+    if (p.clocks)
+      for (int i = 0; i < 6; ++i) p.ctrl[8 + i] = tph[i];
   }
 #undef KL_PHASE
+}
+
+// Best-prefix rollback (the classic KL pass ends by keeping only the swaps up to the best cut -- the
+// reference tracks minCutSize, cKL.cpp:363, but never rolls back nor saves the partition, cKL.cpp:395-405): swaps
+// best+1 .. swaps of the last pass are undone on the device.  Returns the kept row (first minimum of the cut column).
+__global__ void kl_undo_kernel(const int32_t *__restrict__ n1, const int32_t *__restrict__ n2, int64_t from, int64_t to,
+                               uint8_t *__restrict__ state) {
+  const int64_t i = from + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > to) return;
+  state[n1[i]] = (uint8_t)ST_LOCK;                   // back on side 0 (still marked: the pass is over)
+  state[n2[i]] = (uint8_t)(ST_SIDE | ST_LOCK);       // back on side 1
+}
+int64_t kl_rollback(eigkl_handle *h, float *best_cut) {
+  auto &k = h->kl;
+  EIGKL_REQUIRE(k.have_partition && k.consumed, EIGKL_E_ARG, "eigkl_kl_rollback: no finished KL pass to roll back");
+  std::vector<float> cut((size_t)k.swaps + 1);
+  EIGKL_CUDA(cudaMemcpyAsync(cut.data(), k.t_cut.p, cut.size() * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+  EIGKL_CUDA(cudaStreamSynchronize(h->stream));
+  int64_t best = 0;
+  for (int64_t i = 1; i <= k.swaps; ++i)
+    if (cut[(size_t)i] < cut[(size_t)best]) best = i;                 // first minimum
+  if (best < k.swaps) {
+    kl_undo_kernel<<<grid_for(k.swaps - best), TPB, 0, h->stream>>>(k.t_n1.p, k.t_n2.p, best + 1, k.swaps, k.state.p);
+    h->launches++;
+    EIGKL_CUDA(cudaGetLastError());
+  }
+  k.swaps = best;                                                    // a second rollback is a no-op
+  if (best_cut) *best_cut = cut[(size_t)best];
+  return best;
 }
 
 void kl_run(eigkl_handle *h) {
@@ -1073,6 +1099,7 @@ void kl_run(eigkl_handle *h) {
     q.state = k.state.p; q.rank = k.rank.p; q.val = k.val.p; q.order0 = k.order0.p; q.order1 = k.order1.p;
     q.t_cut = k.t_cut.p; q.t_gain = k.t_gain.p; q.t_n1 = k.t_n1.p; q.t_n2 = k.t_n2.p;
     q.ctrl = k.ctrl.p; q.cut0 = cut0; q.term_limit = p.term_limit; q.n0 = k.n0; q.n1 = k.n1;
+    q.clocks = getenv("EIGKL_KL_PHASES") != nullptr ? 1 : 0;
     const size_t smem = (size_t)n_tiles * (16 + 4 + 4) + (gbits ? 0 : (size_t)((n + 15) / 16) * 4) + 16;
     if (!h->attr_kl_local) {
       const size_t max_smem = std::max((size_t)(KL_LOCAL_MAX_N / KL_TILE) * 24 + (size_t)(KL_LOCAL_MAX_N / 16) * 4,
@@ -1131,8 +1158,8 @@ void kl_run(eigkl_handle *h) {
   k.swaps = ctrl[0];
   k.consumed = true;
   h->stats.kl_swaps = k.swaps;
-  if (getenv("EIGKL_KL_PHASES") && R == 1 && !local && k.swaps > 0) {   // the global-memory loop carries the clocks
-    static const char *nm[6] = {"S1 reduce", "decode", "S3 own rows", "S3 barrier wait", "S4 own tiles", "S4 barrier wait"};
+  if (getenv("EIGKL_KL_PHASES") && R == 1 && k.swaps > 0) {
+    static const char *nm[6] = {"S1 reduce", "decode + row pointers", "S3 own rows", "S3 barrier wait", "S4 own tiles", "S4 barrier wait"};
     fprintf(stderr, "[eigkl] KL phases, cycles per swap (thread 0):");
     for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f;", nm[i], (double)ctrl[8 + i] / (double)k.swaps);
     fprintf(stderr, "\n");

@@ -191,6 +191,13 @@ int  eigkl_write_trace(const char *path, const eigkl_trace *trace);
 /* current side of every node (after eigkl_kl_run: the final partition, which the reference never
  * writes anywhere -- SURVEY.md section 8f.3)                                                     */
 int  eigkl_get_partition(eigkl_handle *h, uint8_t *side);
+/* Extensions the reference stops short of (cKL.cpp:363 tracks the best cut, cKL.cpp:395-405
+ * neither rolls back to it nor saves the partition).  eigkl_kl_rollback undoes, on the device, the swaps after the
+ * first minimum of the last pass' cut column and reports that row / cut; eigkl_write_partition writes "<node>\t<side>"
+ * per line (0-based ids, ascending).  Calling eigkl_kl_run again without a new partition starts a NEW pass from the
+ * current sides with fresh locks and ascending remain[] lists, as KL() does on every call (cKL.cpp:290-301).           */
+int  eigkl_kl_rollback(eigkl_handle *h, int64_t *best_row, float *best_cut);
+int  eigkl_write_partition(eigkl_handle *h, const char *path);
 
 /* ---- test / measurement hooks ------------------------------------------------------------------ */
 int  eigkl_spmv(eigkl_handle *h, const double *x, double *y);                 /* y = L x (host buffers) */

@@ -79,3 +79,40 @@ def test_cli_errors(eigkl_lib, workdir, tmp_path):
     assert r.returncode == 1 and "EIG file not found" in r.stderr                        # cKL.cpp:157-160
     r = run("cKL", ["circuit/fract.hgr"], wd)                                            # random branch runs
     assert r.returncode == 0 and os.path.exists(os.path.join(wd, "results", "fract.hgr_KL_CutSize_output.txt"))
+
+
+def test_seed_rollback_and_partition_flags(eigkl_lib, workdir, tmp_path, oracle):
+    """--seed makes the random branch (cKL.cpp:175-193) repeatable; --rollback keeps the best prefix
+    of the pass (the reference tracks minCutSize, cKL.cpp:363, and stops there); --partition-out saves the sides."""
+    import shutil
+    import numpy as np
+    wd = str(tmp_path)
+    os.makedirs(os.path.join(wd, "circuit"))
+    os.makedirs(os.path.join(wd, "pre_saved_EIG"))
+    shutil.copy(os.path.join(workdir, "circuit", "ibm01.hgr"), os.path.join(wd, "circuit", "ibm01.hgr"))
+    shutil.copy(os.path.join(workdir, "pre_saved_EIG", "ibm01.hgr_out.txt"), os.path.join(wd, "pre_saved_EIG", "ibm01.hgr_out.txt"))
+    trace = os.path.join(wd, "results", "ibm01.hgr_KL_CutSize_output.txt")
+    outs = []
+    for seed, pout in (("7", "p7a.txt"), ("7", "p7b.txt"), ("8", "p8.txt")):
+        r = run("cKL", ["circuit/ibm01.hgr", "--seed", seed, "--partition-out", pout], wd)
+        assert r.returncode == 0, r.stderr
+        outs.append((open(trace, "rb").read(), open(os.path.join(wd, pout), "rb").read()))
+    assert outs[0] == outs[1]                    # same seed: identical trace and partition files
+    assert outs[0][0] != outs[2][0]              # another seed: another start
+    # --rollback from the golden start: the saved partition is the start with swaps 1..best applied
+    r = run("cKL", ["circuit/ibm01.hgr", "-EIG", "--rollback"], wd)
+    assert r.returncode == 0, r.stderr
+    got = open(os.path.join(wd, "results", "ibm01.hgr_KL_CutSize_EIG_output.txt"), "rb").read()
+    assert got == open(os.path.join(GOLDEN, "ibm01.kl_trace_1core.txt"), "rb").read()      # the trace itself is unchanged
+    part = np.loadtxt(os.path.join(wd, "results", "ibm01.hgr_KL_partition_EIG.txt"), dtype=np.int64)
+    g = oracle.read_eig(os.path.join(wd, "pre_saved_EIG", "ibm01.hgr_out.txt"), 12752)
+    ro = oracle.OracleKL(oracle.OracleHgr(os.path.join(wd, "circuit", "ibm01.hgr"))).run(g["side"])
+    best = int(np.argmin(ro["cut"]))             # first minimum
+    expect = g["side"].copy()
+    expect[ro["node1"][1:best + 1]] = 1
+    expect[ro["node2"][1:best + 1]] = 0
+    assert np.array_equal(part[:, 0], np.arange(12752)) and np.array_equal(part[:, 1].astype(np.uint8), expect)
+    assert 0 < best < ro["swaps"] and int(expect.sum()) == int(g["side"].sum())
+    # the reference's own argv forms are untouched by the extensions
+    r = run("cKL", ["circuit/ibm01.hgr", "-EIG", "extra"], wd)
+    assert r.returncode == 1 and "Usage:" in r.stdout

@@ -233,9 +233,39 @@ def test_bad_inputs_are_rejected(tmp_path):
         with pytest.raises(api.EigklError) as e:
             h.load_hgr(str(tmp_path / "missing.hgr"))
         assert e.value.code == -2
+        with pytest.raises(api.EigklError) as e:                        # offsets that go backwards: negative net sizes
+            h.set_pins(4, np.array([0, 3, 2, 4], np.int64), np.array([0, 1, 2, 3], np.int32))
+        assert e.value.code == -3
         h.set_pins(4, off, np.array([0, 1, 2], np.int32))
         with pytest.raises(api.EigklError):
             h.kl_run()                                                   # no graph / partition yet
+
+
+def test_second_pass_without_new_partition_is_a_real_pass(handles, oracle, circuits, workdir):
+    """KL() rebuilds remain[] / split[] from the current sides on every call (cKL.cpp:290-301): a second eigkl_kl_run
+    without a new partition starts from the FINAL partition of the first, with fresh locks and ascending orders."""
+    import ctypes as C
+    c = "ibm01"
+    h = handles[c]
+    h.assemble_kl_graph()
+    h.load_eig(datasets.golden_eig_path(workdir, c))
+    tr1 = h.kl_run()
+    side1 = h.get_partition()
+    tr2 = h.kl_run()                                                     # no set_partition in between
+    o = oracle.OracleKL(oracle.OracleHgr(circuits[c]))
+    ro = o.run(side1)
+    assert tr2["swaps"] == ro["swaps"] and np.array_equal(tr2["node1"], ro["node1"]) and np.array_equal(tr2["node2"], ro["node2"])
+    assert np.array_equal(tr2["cut"].view(np.uint32), ro["cut"].view(np.uint32))
+    assert np.array_equal(h.get_partition(), ro["side"])
+    # cut / D-values after a pass describe the final partition too
+    assert h.cut().view(np.uint32) == o.cut0(ro["side"]).view(np.uint32)
+    assert np.array_equal(h.dvalues().view(np.uint32), o.dvalues(ro["side"]).view(np.uint32))
+    # a trace that is too short is refused before the pass runs
+    h.load_eig(datasets.golden_eig_path(workdir, c))
+    cut = np.zeros(4, np.float32)
+    t = api.Trace(4, 0, cut.ctypes.data_as(C.POINTER(C.c_float)), None, None, None)
+    assert h.lib.eigkl_kl_run(h._h, C.byref(t)) == -1
+    assert h.stats()["kl_swaps"] == tr2["swaps"]                         # nothing ran
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -279,6 +309,36 @@ def test_fiedler_ibm10_residual(handles, oracle, circuits):
     lam, v = h.fiedler()
     assert abs(lam - 0.0185035852) / 0.0185035852 < 1e-7                  # converged lambda2, SURVEY Appendix D
     assert np.linalg.norm(h.spmv(v) - lam * v) < 1e-9
+
+
+def test_fiedler_ibm10_vs_independent_solve(oracle, circuits):
+    """ibm10's Fiedler VECTOR against an independent converged solve: the oracle port's plain restarted Lanczos on the
+    CPU (different algorithm -- no polynomial filter --, different code, different arithmetic order)."""
+    with api.Handle() as h:
+        h.load_hgr(circuits["ibm10"])
+        h.assemble_laplacian()
+        lam, v = h.fiedler()
+    e = oracle.OracleEIG(oracle.OracleHgr(circuits["ibm10"]))
+    lo, vo, st = e.fiedler()
+    assert st["converged"] == 1
+    assert np.linalg.norm(e.spmv(vo) - lo * vo) < 1e-8                   # the independent pair is a genuine eigenpair
+    assert abs(lam - lo) / lo <= 1e-8                                    # north star: 1e-8 relative
+    cs = abs(v @ vo)
+    assert np.sqrt(max(0.0, 1.0 - cs * cs)) <= 1e-6                      # north star: 1e-6 sine
+
+
+def test_fiedler_sign_is_canonical(circuits):
+    """The returned vector's largest-magnitude component is positive, whatever the start vector: the side labels
+    (and the fused EIG -> KL trace) do not depend on the seed or on the number of ranks."""
+    vs = []
+    for seed in (0, 1, 12345):
+        with api.Handle(seed=seed) as h:
+            h.load_hgr(circuits["ibm01"])
+            h.assemble_laplacian()
+            lam, v = h.fiedler()
+            vs.append(v)
+        assert v[np.argmax(np.abs(v))] > 0
+    assert v @ vs[0] > 0.999999 and vs[1] @ vs[0] > 0.999999
 
 
 def test_fiedler_is_reproducible(handles):
