@@ -65,7 +65,7 @@ class Stats(C.Structure):
                 ("bytes_multidot_total", C.c_double), ("bytes_update_total", C.c_double),
                 ("spmv_per_launch", C.c_int32), ("resident_k", C.c_int32),
                 ("gs_fused", C.c_int32), ("gs_cache_cols", C.c_int32),
-                ("kl_local", C.c_int32), ("reserved0", C.c_int32),
+                ("kl_local", C.c_int32), ("kl_flat", C.c_int32),
                 ("dist_ranks", C.c_int32), ("dist_rows", C.c_int32), ("dist_halo", C.c_int64), ("dist_exports", C.c_int64),
                 ("ms_comm", C.c_double), ("ms_push", C.c_double), ("n_comm", C.c_int64), ("n_push", C.c_int64)]
 

@@ -7,6 +7,7 @@
 
 int main(int argc, char *argv[]) {
   auto t0 = std::chrono::high_resolution_clock::now();
+  StageClock clk;
   eigkl_handle *h = nullptr;
   auto fail = [&](const std::string &what) {
     std::cerr << "Error: " << what << std::endl;        // cEIG.cpp:231-234
@@ -22,19 +23,24 @@ int main(int argc, char *argv[]) {
   o.struct_size = sizeof(o);
   o.device = device_from_env();
   if (eigkl_create(&h, &o) != EIGKL_OK) return fail(eigkl_last_error(nullptr));
+  clk.tick("eigkl_create (CUDA context)");
   std::cout << "\n============= Initialization =============\n";
   std::cout << "Backend: libeigkl (CUDA, sm_100a), ABI " << eigkl_abi_version() << std::endl;
   if (eigkl_load_hgr(h, filename.c_str()) != EIGKL_OK) return fail(eigkl_last_error(h));
   int32_t nodes = 0, nets = 0;
   eigkl_get_sizes(h, &nodes, &nets, nullptr);
   std::cout << "\nProblem Size:\n  - Nets: " << nets << "\n  - Nodes: " << nodes << "\n";
+  clk.tick("eigkl_load_hgr");
   std::cout << "\nInitializing sparse matrix...\n";
   if (eigkl_assemble_laplacian(h) != EIGKL_OK) return fail(eigkl_last_error(h));
+  clk.tick("eigkl_assemble_laplacian");
   std::cout << "Computing eigenvalues...\n";
   double lambda2 = 0;
   if (eigkl_fiedler(h, &lambda2, nullptr) != EIGKL_OK) return fail(std::string("Eigenvalue computation failed: ") + eigkl_last_error(h));
+  clk.tick("eigkl_fiedler");
   std::cout << "\nWriting results...\n";
   if (eigkl_write_eig(h, outfile.c_str()) != EIGKL_OK) return fail(eigkl_last_error(h));
+  clk.tick("eigkl_write_eig");
   eigkl_stats st{};
   st.struct_size = sizeof(st);
   eigkl_get_stats(h, &st);

@@ -47,6 +47,7 @@ inline int kl_main(int argc_all, char *argv_all[], bool gkl_flavour) {
     eig_file = "pre_saved_EIG/" + base + "_out.txt";
     fout_name = "results/" + base + "_KL_CutSize_EIG_output.txt";
   }
+  StageClock clk;
   eigkl_handle *h = nullptr;
   auto fail = [&](const std::string &what) {
     std::cerr << what << std::endl;
@@ -57,15 +58,18 @@ inline int kl_main(int argc_all, char *argv_all[], bool gkl_flavour) {
   o.struct_size = sizeof(o);
   o.device = device_from_env();
   if (eigkl_create(&h, &o) != EIGKL_OK) return fail(std::string("Error occurred: ") + eigkl_last_error(nullptr));
+  clk.tick("eigkl_create (CUDA context)");
   std::cout << "\n============= Reading Input File ==============\n";
   if (eigkl_load_hgr(h, input_file.c_str()) != EIGKL_OK) {
     const std::string e = eigkl_last_error(h);
     return fail(e.rfind("Error opening", 0) == 0 ? "Error opening file: " + input_file : "Error occurred: " + e);   // cKL.cpp:87-90
   }
+  clk.tick("eigkl_load_hgr");
   int32_t nodes = 0, nets = 0;
   eigkl_get_sizes(h, &nodes, &nets, nullptr);
   std::cout << "Circuit Statistics\n  - Total Nets : " << nets << "\n  - Total Nodes: " << nodes << "\n";
   if (eigkl_assemble_kl_graph(h) != EIGKL_OK) return fail(std::string("Error occurred: ") + eigkl_last_error(h));
+  clk.tick("eigkl_assemble_kl_graph");
   std::cout << "\n\n=========== Starting KL Algorithm =============\n";
   int64_t n0 = 0, n1 = 0;
   if (eig_init) {
@@ -85,6 +89,7 @@ inline int kl_main(int argc_all, char *argv_all[], bool gkl_flavour) {
     n0 = nodes / 2; n1 = nodes - n0;
     if (eigkl_set_partition_ordered(h, ids.data(), n0, ids.data() + n0, n1) != EIGKL_OK) return fail(std::string("Error occurred: ") + eigkl_last_error(h));
   }
+  clk.tick("initial partition");
   std::cout << "Partition sizes - Left: " << n0 << " Right: " << n1 << std::endl;
   const int64_t cap = std::min(n0, n1) + 1;
   std::vector<float> cut((size_t)cap), gain((size_t)cap);
@@ -94,7 +99,9 @@ inline int kl_main(int argc_all, char *argv_all[], bool gkl_flavour) {
   auto t0 = std::chrono::high_resolution_clock::now();
   if (eigkl_kl_run(h, &tr) != EIGKL_OK) return fail(std::string("Error occurred: ") + eigkl_last_error(h));
   auto t1 = std::chrono::high_resolution_clock::now();
+  clk.tick("eigkl_kl_run");
   if (eigkl_write_trace(fout_name.c_str(), &tr) != EIGKL_OK) return fail("Error: Cannot open output file");   // cKL.cpp:296-299
+  clk.tick("eigkl_write_trace");
   eigkl_stats st{};
   st.struct_size = sizeof(st);
   eigkl_get_stats(h, &st);
@@ -120,5 +127,6 @@ inline int kl_main(int argc_all, char *argv_all[], bool gkl_flavour) {
             << " (GPU: setup " << st.ms_kl_setup << " ms, swap loop " << st.ms_kl_loop << " ms)\n";
   std::cout << std::left << std::setw(24) << "Trace written to" << ": " << fout_name << "\n";
   eigkl_destroy(h);
+  clk.tick("eigkl_destroy");
   return 0;
 }

@@ -567,7 +567,8 @@ void assemble_kl_graph(eigkl_handle *h) {
   } else {
     EIGKL_CUDA(cudaMemsetAsync(A.fwd_end.p, 0, (size_t)n * sizeof(int32_t), h->stream));
   }
-  const int64_t chunk = pick_chunk(h, A.nnz, 8);
+  // the D-value kernel stages a block's 2048 signed weights: leave room for the block's last row
+  const int64_t chunk = std::min<int64_t>(pick_chunk(h, A.nnz, 8), 1792);
   A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz, chunk));
   A.blk_row.alloc((size_t)A.n_blocks + 1);
   row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, 0, n, chunk, A.n_blocks, A.blk_row.p);
@@ -575,6 +576,7 @@ void assemble_kl_graph(eigkl_handle *h) {
   EIGKL_CUDA(cudaGetLastError());
   A.valid = true;
   A.nb_valid = false;
+  A.info_valid = false;
   h->stats.nnz_kl = A.nnz;
   // algorithmic bytes of one full D-value pass: nnz*(4 w + 4 col) + n*(4 rowptr + 1 side + 4 out)  
   h->stats.bytes_dvalues = (double)A.nnz * 8.0 + (double)n * 9.0;

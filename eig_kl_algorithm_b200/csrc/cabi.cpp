@@ -135,6 +135,7 @@ int eigkl_create(eigkl_handle **out, const eigkl_opts *opts) {
     if (const char *m = getenv("EIGKL_SPMV_RESIDENT")) h->spmv_resident = atoi(m);
     if (const char *m = getenv("EIGKL_GS_FUSED")) h->gs_fused = atoi(m);
     if (const char *m = getenv("EIGKL_KL_LOCAL")) h->kl_local = atoi(m);
+    if (const char *m = getenv("EIGKL_KL_FLAT")) h->kl_flat = atoi(m);
     if (const char *m = getenv("EIGKL_DIST")) {       // rows | replicate | auto
       h->dist_mode = (strcmp(m, "rows") == 0 || strcmp(m, "1") == 0) ? 1 : (strcmp(m, "replicate") == 0 || strcmp(m, "2") == 0) ? 2 : 0;
     }

@@ -238,11 +238,14 @@ struct KlCsr {                 // fp32, symmetric, rows in reference traversal o
   DBuf<int32_t> blk_row;
   DBuf<int32_t> nb;            // 2 per entry: rowptr[col], rowptr[col + 1] (the shared-memory swap loop's one-load lookup)
   bool nb_valid = false;
+  DBuf<int32_t> blk_info;      // 4 ints per row block of the D-value kernel: r0, r1, first entry, end entry
+  bool info_valid = false;
   bool valid = false;
 };
 
 struct KlState {
   DBuf<uint8_t> state;         // bit0 = side, bit1 = locked
+  DBuf<uint32_t> side_bits;    // the sides as a bitmap (1 bit per node), packed when a partition is set: the D-value kernel's gather source
   DBuf<uint32_t> rank;         // position in remain[side] (ties -> lowest rank)
   DBuf<float> val;             // connections(v)
   DBuf<unsigned long long> tile_key;   // 2 * n_tiles
@@ -316,9 +319,10 @@ struct eigkl_handle {
   int spmv_resident = 1;       // EIGKL_SPMV_RESIDENT=0: one launch per SpMV even when the matrix fits on chip
   int gs_fused = 1;            // EIGKL_GS_FUSED=0: Gram-Schmidt as separate multidot / update launches
   // per-handle (= per-device) one-time kernel attribute set-up, and what the device allows
-  bool attr_kl_local = false, attr_gs = false, attr_resident = false;
+  bool attr_kl_local = false, attr_kl_flat = false, attr_gs = false, attr_resident = false;
   int coop_ok = -1;            // -1 unknown, 0/1: cudaDevAttrCooperativeLaunch
   int kl_local = 1;            // EIGKL_KL_LOCAL=0: never run the swap loop with its state in shared memory
+  int kl_flat = 1;             // EIGKL_KL_FLAT=0: the warp-per-row form of the shared-memory swap loop (kl_loop_local_kernel)
   void *nccl_comm = nullptr;   // ncclComm_t when nranks > 1
   void *l2_flush = nullptr;    // >L2 scratch for eigkl_time_kernel
   // scratch of the sort / scan primitives

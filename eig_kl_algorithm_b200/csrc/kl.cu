@@ -145,14 +145,101 @@ static void kl_rearm(eigkl_handle *h) {
   kl_set_partition_device(h, side.p);
 }
 
+// Second form (default).  The first one gathers one side BYTE per entry -- a 32-byte sector of L2 traffic per
+// useful byte, 352 MB on top of the 88 MB of (col, w) at 2 M nodes -- after two dependent loads just to find its
+// row block (0.22 of the HBM peak there, 0.11 on ibm10).  Here:
+//   * the sides are a BITMAP (1 bit per node, packed when the partition is set: 252 KB at 2 M nodes), read
+//     through the read-only path: after the first touches an SM's L1 holds it, so the gathers stop reaching L2;
+//   * a CTA reads ONE int4 descriptor (rows and entry range), then issues all its loads in one round -- 8
+//     (col, w) pairs per thread, the row pointers into shared memory -- then the bit gathers, stages the signed
+//     weights, and one thread per row adds its run in order (two fp32 accumulators, cKL.cpp:225-251).
+constexpr int KLD_K = 8;
+__global__ void __launch_bounds__(KLD_THREADS)
+dvalues_bits_kernel(const int4 *__restrict__ info, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                    const float *__restrict__ w, const uint32_t *__restrict__ side_bits, const uint8_t *__restrict__ state,
+                    float *__restrict__ val) {
+  __shared__ float sv[KLD_THREADS * KLD_K];
+  __shared__ int32_t rp[KLD_THREADS * KLD_K + 1];
+  const int tid = threadIdx.x;
+  const int4 bi = __ldg(info + blockIdx.x);
+  const int32_t r0 = bi.x, r1 = bi.y, e0 = bi.z, e1 = bi.w;
+  if (r0 >= r1) return;
+  const int32_t span = e1 - e0, nrows = r1 - r0;
+  if (span <= KLD_THREADS * KLD_K) {
+    int32_t c[KLD_K];
+    float ww[KLD_K];
+#pragma unroll
+    for (int k = 0; k < KLD_K; ++k) {
+      const int32_t i = tid + k * KLD_THREADS;
+      c[k] = -1; ww[k] = 0.0f;
+      if (i < span) { c[k] = __ldcs(col + e0 + i); ww[k] = __ldcs(w + e0 + i); }
+    }
+    for (int32_t rr = tid; rr <= nrows; rr += KLD_THREADS) rp[rr] = __ldg(rowptr + r0 + rr) - e0;
+#pragma unroll
+    for (int k = 0; k < KLD_K; ++k) {
+      const int32_t i = tid + k * KLD_THREADS;
+      if (c[k] >= 0) sv[i] = ((__ldg(side_bits + (c[k] >> 5)) >> (c[k] & 31)) & 1u) ? ww[k] : -ww[k];
+    }
+    __syncthreads();
+    for (int32_t rr = tid; rr < nrows; rr += KLD_THREADS) {
+      const int32_t lo = rp[rr], hi = rp[rr + 1];
+      float E = 0.0f, I = 0.0f;
+      for (int32_t i = lo; i < hi; ++i) {
+        const float x = sv[i];
+        E = __fadd_rn(E, fmaxf(x, 0.0f));
+        I = __fadd_rn(I, fmaxf(-x, 0.0f));
+      }
+      val[r0 + rr] = __fsub_rn(E, I);
+    }
+  } else {                              // a row longer than the staging buffer lives here
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int32_t r = r0 + warp; r < r1; r += KLD_THREADS / 32) {
+      const float v = warp_row_value(col, w, state, rowptr[r], rowptr[r + 1], -1, -1, lane);
+      if (lane == 0) val[r] = v;
+    }
+  }
+}
+__global__ void kl_blk_info_kernel(const int32_t *__restrict__ blk_row, const int32_t *__restrict__ rowptr, int32_t n_blocks,
+                                   int4 *__restrict__ info) {
+  const int32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_blocks) return;
+  const int32_t r0 = blk_row[b], r1 = blk_row[b + 1];
+  info[b] = make_int4(r0, r1, rowptr[r0], rowptr[r1]);
+}
+// 32 nodes per warp: the side bits of the state bytes, one word per ballot
+__global__ void pack_side_bits_kernel(const uint8_t *__restrict__ state, int32_t n, uint32_t *__restrict__ out) {
+  const int32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned bit = (v < n) ? ((unsigned)state[v] & ST_SIDE) : 0u;
+  const unsigned word = __ballot_sync(FULL_MASK, bit != 0u);
+  if ((threadIdx.x & 31) == 0 && (v >> 5) <= ((n - 1) >> 5)) out[v >> 5] = word;
+}
+static void kl_pack_sides(eigkl_handle *h) {
+  auto &k = h->kl;
+  const int32_t n = h->hg.n_nodes;
+  k.side_bits.ensure((size_t)(n + 31) / 32 + 1);
+  pack_side_bits_kernel<<<grid_for((int64_t)((n + 31) / 32) * 32), TPB, 0, h->stream>>>(k.state.p, n, k.side_bits.p);
+  h->launches++;
+}
+
 void kl_dvalues(eigkl_handle *h) {
   auto &A = h->A;
   auto &k = h->kl;
   EIGKL_REQUIRE(A.valid, EIGKL_E_ARG, "KL graph not assembled");
   EIGKL_REQUIRE(k.have_partition, EIGKL_E_ARG, "no partition set");
   kl_rearm(h);
+  static const bool old_form = getenv("EIGKL_DVALUES_BYTES") != nullptr;     // tuning aid: the byte-gather kernel
+  if (!old_form && !A.info_valid) {
+    A.blk_info.alloc((size_t)4 * A.n_blocks + 4);
+    kl_blk_info_kernel<<<grid_for(A.n_blocks), TPB, 0, h->stream>>>(A.blk_row.p, A.rowptr.p, A.n_blocks, reinterpret_cast<int4 *>(A.blk_info.p));
+    h->launches++;
+    A.info_valid = true;
+  }
   h->prof.begin(KC_DVALUES, h->stream);
-  dvalues_kernel<<<(unsigned)A.n_blocks, KLD_THREADS, 0, h->stream>>>(A.rowptr.p, A.col.p, A.w.p, k.state.p, k.val.p, A.blk_row.p);
+  if (old_form)
+    dvalues_kernel<<<(unsigned)A.n_blocks, KLD_THREADS, 0, h->stream>>>(A.rowptr.p, A.col.p, A.w.p, k.state.p, k.val.p, A.blk_row.p);
+  else
+    dvalues_bits_kernel<<<(unsigned)A.n_blocks, KLD_THREADS, 0, h->stream>>>(reinterpret_cast<const int4 *>(A.blk_info.p), A.rowptr.p, A.col.p,
+                                                                          A.w.p, k.side_bits.p, k.state.p, k.val.p);
   h->prof.end(h->stream);
   h->launches++;
   EIGKL_CUDA(cudaGetLastError());
@@ -196,7 +283,7 @@ static void kl_alloc_state(eigkl_handle *h, int32_t n) {
   const int64_t n_tiles = ceil_div(n, KL_TILE);
   k.tile_key.ensure((size_t)(2 * n_tiles + 2 * KL_MAX_CLUSTER + 8));
   k.tile_stamp.ensure((size_t)n_tiles + 1);
-  k.ctrl.ensure(16);
+  k.ctrl.ensure(40);
 }
 
 void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
@@ -216,6 +303,7 @@ void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   EIGKL_REQUIRE(herr == 0, EIGKL_E_FORMAT, "partition side not in {0,1}");
   k.n0 = n0; k.n1 = n - n0; k.ascending = true; k.have_partition = true; k.consumed = false;
+  kl_pack_sides(h);
 }
 
 void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *order0, int64_t n0,
@@ -246,6 +334,7 @@ void kl_set_partition(eigkl_handle *h, const uint8_t *side_host, const int32_t *
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   EIGKL_REQUIRE(herr == 0, EIGKL_E_ARG, "orders must cover every node exactly once");
   k.n0 = n0; k.n1 = n1; k.ascending = false; k.have_partition = true; k.consumed = false;
+  kl_pack_sides(h);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -842,6 +931,11 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
   long long tph[6] = {0, 0, 0, 0, 0, 0};
   long long tprev = clock64();
 #define KL_PHASE(i) do { if (p.clocks && tid == 0) { const long long t_ = clock64(); tph[i] += t_ - tprev; tprev = t_; } } while (0)
+  // finer probes (thread 0, shared-memory accumulators so that they cost no registers): ctrl[16 + i]
+  __shared__ long long sh_fine[16];
+  __shared__ long long sh_fprev;
+  if (tid == 0) { for (int i = 0; i < 16; ++i) sh_fine[i] = 0; sh_fprev = clock64(); }
+#define KL_FINE(i) do { if (p.clocks && tid == 0) { const long long t_ = clock64(); sh_fine[i] += t_ - sh_fprev; sh_fprev = t_; } } while (0)
 
   while (!sh_done) {
     // ---- S1: best pair over the tile keys (shared memory) ----
@@ -855,13 +949,17 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
     k1 = warp_max_u64(k1);
     if (lane == 0) { red0[warp] = k0; red1[warp] = k1; }
     if (tid == 0) sh_nlist = 0;
+    KL_FINE(0);
     __syncthreads();
+    KL_FINE(1);
     if (warp == 0) {
       k0 = warp_max_u64(red0[lane]);
       k1 = warp_max_u64(red1[lane]);
       if (lane == 0) { sh_best[0] = k0; sh_best[1] = k1; }
     }
+    KL_FINE(2);
     __syncthreads();
+    KL_FINE(3);
     const unsigned long long b0 = sh_best[0], b1 = sh_best[1];
     if (b0 == 0ull || b1 == 0ull) {                  // no selectable node on one side (cKL.cpp:387-389)
       if (tid == 0) sh_done = 1;
@@ -877,6 +975,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
     const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
     const int32_t da = ahi - alo, items = da + (bhi - blo);
     KL_PHASE(1);
+    KL_FINE(4);
     constexpr int WORKERS = KL_LOOP_THREADS / 32 - 1;    // warp 31 is the bookkeeper
     const uint32_t stamp = it_local;
     if (warp == WORKERS) {
@@ -927,6 +1026,8 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
         uint32_t my_id = (uint32_t)my_v;
         if (!ASC && kidx < n_mine) my_id = __ldg(p.rank + my_v);
         const int cnt = min(32, n_mine - k0i);
+        if (p.clocks && tid == 0 && my_ext.x + my_v == -12345) sh_fine[15] = 1;     // a use of the loaded values: the probe below sees their arrival
+        KL_FINE(5);
         for (int j0 = 0; j0 < cnt; j0 += 4) {
           int32_t lo[4], hi[4], c[4];
           float ww[4];
@@ -939,12 +1040,15 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
             c[u] = 0; ww[u] = 0.0f;
             if (lo[u] + lane < hi[u]) { c[u] = __ldg(p.col + lo[u] + lane); ww[u] = __ldg(p.w + lo[u] + lane); }
           }
+          if (p.clocks && tid == 0 && c[0] + c[1] + c[2] + c[3] == -12345) sh_fine[15] = 2;
+          KL_FINE(6);
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (j0 + u < cnt) {                                    // warp-uniform
               const int32_t v = __shfl_sync(FULL_MASK, my_v, j0 + u);
               const uint32_t vid = __shfl_sync(FULL_MASK, my_id, j0 + u);
               const float nv = warp_row_value_local<GBITS>(p.col, p.w, bits, p.state, lo[u], hi[u], a, b, lane, c[u], ww[u], sh_wsm[warp]);
+              KL_FINE(7);
               if (lane == 0) {
                 __stcg(p.val + v, nv);
                 const unsigned st = kl_state_get<GBITS>(bits, p.state, v);
@@ -960,30 +1064,411 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
                   }
                 }
               }
+              KL_FINE(8);
             }
           }
         }
       }
     }
     KL_PHASE(2);
+    KL_FINE(9);
     __syncthreads();
     KL_PHASE(3);
+    KL_FINE(10);
     // ---- S4: rescan the few tiles whose best node was touched or locked, one per warp ----
     {
       const int nl = sh_nlist;
+      if (p.clocks && tid == 0) sh_fine[14] += nl;
       for (int q = warp; q < nl; q += KL_LOOP_THREADS / 32)
         tile_scan_local<ASC, GBITS>(bits, p.state, p.val, p.rank, p.n, list[q], lane, keys);
     }
     KL_PHASE(4);
+    KL_FINE(11);
     __syncthreads();
     KL_PHASE(5);
+    KL_FINE(12);
   }
   if (tid == 0) {
     p.ctrl[0] = (int64_t)sh_iter; p.ctrl[1] = 1;
-    if (p.clocks)
+    if (p.clocks) {
       for (int i = 0; i < 6; ++i) p.ctrl[8 + i] = tph[i];
+      for (int i = 0; i < 16; ++i) p.ctrl[16 + i] = sh_fine[i];
+    }
   }
 #undef KL_PHASE
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The swap loop, third form ("flat"): the same state in shared memory as kl_loop_local_kernel, restructured after
+// its phase clocks (ibm10, cycles per swap of ~9 400: S1 1 500; row pointers 730; neighbour entries 830; neighbour
+// rows 1 000; the two ordered row sums of the slowest warp 2 200 + 730 of epilogue; tile rescans 1 800 behind a
+// barrier; every dependent global load costs 700-1 000 cycles from a lone CTA, not the 250 of an L2 hit):
+//   * 512 threads.  Item i of N(a) ++ N(b) belongs to lane i/15 of warp i%15, so a warp OWNS its rows: it loads
+//     their entries (all rows and all 32-entry chunks in flight at once), stages the signed weights in its private
+//     slice of shared memory
+//     and then every lane adds ITS row serially -- the fp32 order of cKL.cpp:225-251 -- with all rows of the block
+//     summed concurrently (~20 dependent FADD pairs) instead of one row per warp at a time.  No block barrier
+//     inside the phase; a warp whose rows exceed its slice falls back to the warp-per-row replay.
+//   * pair selection is two-level: keys per 256-node tile and per group of 32 tiles; EVERY warp folds the group
+//     keys itself (no broadcast barrier), a raised key raises its group in place, and only groups whose tiles were
+//     rescanned are recomputed.
+//   * the tiles of a and b always need a rescan (their best nodes were just locked): their D-values are loaded
+//     at the START of the swap by two otherwise idle warps and patched after the row sums with the values
+//     recomputed in this swap (a 256-entry patch slice per tile), so that rescan costs no round trip of its own.
+//   * a neighbour that holds its tile's best key forces a rescan only when its key went DOWN; a raised holder is
+//     updated in place.
+// The arithmetic is untouched: traces stay byte-identical (test_kl_loop_variants_byte_exact).
+// ---------------------------------------------------------------------------------------------------
+constexpr int KLF_THREADS = 512;
+constexpr int KLF_WARPS = KLF_THREADS / 32;
+constexpr int KLF_ROW_WARPS = KLF_WARPS - 1;   // warps that own neighbour rows; the last warp keeps the books
+constexpr int KLF_MAXN = KLF_ROW_WARPS * 32;   // |N(a)| + |N(b)| handled on the flat path
+constexpr int KLF_WCAP = 384;                  // staged entries per warp
+constexpr int KLF_LCAP = KLF_MAXN + 8;         // late rescans / dirty groups per swap
+constexpr int KL_GROUP = 32;                   // tiles per group key
+
+struct KlFlatSmem {                            // fixed part, placed after the size-dependent arrays
+  float stage[KLF_WARPS][KLF_WCAP];
+  float patch[2][KL_TILE];
+  uint32_t pstamp[2][KL_TILE];
+  int32_t list[2][KLF_LCAP];      // late rescans of a swap, double-buffered by the swap's parity: the counters of the
+  int32_t dlist[2][KLF_LCAP];     // NEXT swap are cleared while this swap's lists are still being read
+  float wab;
+  float cut;
+  uint32_t term, iter;
+  int done, nlist[2], ndirty[2];
+  long long rem0, rem1;
+  long long fine[16];
+  long long fprev;
+};
+
+// What is not on the common path of a swap -- the warp-per-row replay for hub rows, the late tile rescans -- is an
+// out-of-line function with one body shared by its call sites (the loop body is ~30 KB of code as it is).  The
+// update of a node's tile key is on the common path and stays inline (out of line it measured 12 % slower).
+struct KlfCtx {
+  unsigned long long *keys, *gkeys;
+  uint32_t *stamps;
+  KlFlatSmem *S;
+  float *val;
+  int32_t a, b, ta, tb;
+  uint32_t stamp;
+  int par;
+};
+template <bool ASC>
+__device__ __forceinline__ void klf_publish(const KlfCtx &X, int32_t v, uint32_t vid, unsigned st, float nv) {
+  __stcg(X.val + v, nv);
+  if ((st & ST_LOCK) || v == X.a || v == X.b) return;
+  const int32_t tile = v / KL_TILE;
+  KlFlatSmem &S = *X.S;
+  if (tile == X.ta || tile == X.tb) {                 // the early rescan of that tile takes the new value from here
+    const int s = (tile == X.ta) ? 0 : 1;
+    S.patch[s][v % KL_TILE] = nv;
+    S.pstamp[s][v % KL_TILE] = X.stamp;
+    return;
+  }
+  unsigned long long *kp = X.keys + 2 * tile + (st & ST_SIDE);
+  const unsigned long long nk = kl_key<ASC>(nv, st & ST_SIDE, vid);
+  const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+  if (cur != 0ull && (uint32_t)(cur & 0xFFFFFFFFull) == 0xFFFFFFFFu - vid && nk < cur) {
+    // v held the tile's best key and lost ground: the tile is rescanned
+    if (atomicExch(X.stamps + tile, X.stamp) != X.stamp) S.list[X.par][atomicAdd(&S.nlist[X.par], 1)] = tile;
+  } else if (atomicMax(kp, nk) < nk) {
+    atomicMax(X.gkeys + 2 * (tile / KL_GROUP) + (st & ST_SIDE), nk);
+  }
+}
+template <bool ASC, bool GBITS>
+__device__ __noinline__ void klf_row_replay(const KlLocalParams &p, const KlfCtx &X, const uint32_t *bits, int32_t v, uint32_t vid,
+                                            int32_t lo, int32_t hi, float *wsm) {
+  const int lane = threadIdx.x & 31;
+  int32_t c = 0;
+  float ww = 0.0f;
+  if (lo + lane < hi) { c = __ldg(p.col + lo + lane); ww = __ldg(p.w + lo + lane); }
+  const float r = warp_row_value_local<GBITS>(p.col, p.w, bits, p.state, lo, hi, X.a, X.b, lane, c, ww, wsm);
+  if (lane == 0) klf_publish<ASC>(X, v, vid, kl_state_get<GBITS>(bits, p.state, v), r);
+}
+template <bool ASC, bool GBITS>
+__device__ __noinline__ void klf_tile_rescan(const KlLocalParams &p, const uint32_t *bits, int32_t tile, unsigned long long *keys) {
+  tile_scan_local<ASC, GBITS>(bits, p.state, p.val, p.rank, p.n, tile, threadIdx.x & 31, keys);
+}
+
+template <bool ASC, bool GBITS>
+__global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLocalParams p) {
+  extern __shared__ __align__(16) unsigned char kl_sm[];
+  const int32_t n_groups = (p.n_tiles + KL_GROUP - 1) / KL_GROUP;
+  unsigned long long *keys = reinterpret_cast<unsigned long long *>(kl_sm);       // 2 * n_tiles
+  unsigned long long *gkeys = keys + 2 * (size_t)p.n_tiles;                        // 2 * n_groups
+  KlFlatSmem &S = *reinterpret_cast<KlFlatSmem *>(gkeys + 2 * (size_t)n_groups);
+  uint32_t *stamps = reinterpret_cast<uint32_t *>(&S + 1);                         // n_tiles
+  uint32_t *gstamp = stamps + p.n_tiles;                                           // n_groups
+  uint32_t *bits = gstamp + n_groups;                                              // ceil(n / 16) unless GBITS
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) {
+    S.cut = p.cut0; S.term = 0; S.iter = 0; S.rem0 = p.n0; S.rem1 = p.n1; S.wab = 0.0f;
+    S.nlist[0] = S.nlist[1] = 0; S.ndirty[0] = S.ndirty[1] = 0;
+    S.done = (p.n0 <= 0 || p.n1 <= 0) ? 1 : 0;
+    for (int i = 0; i < 16; ++i) S.fine[i] = 0;
+    S.fprev = clock64();
+  }
+  const int32_t n_words = GBITS ? 0 : (p.n + 15) >> 4;
+  for (int32_t wd = tid; wd < n_words; wd += KLF_THREADS) {
+    uint32_t v = 0u;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+      const int32_t u = wd * 16 + q;
+      const unsigned st = u < p.n ? (unsigned)p.state[u] & 3u : ST_LOCK;
+      v |= st << (2 * q);
+    }
+    bits[wd] = v;
+  }
+  for (int32_t t = tid; t < p.n_tiles; t += KLF_THREADS) stamps[t] = 0u;
+  for (int32_t g = tid; g < n_groups; g += KLF_THREADS) gstamp[g] = 0u;
+  for (int i = tid; i < 2 * KL_TILE; i += KLF_THREADS) (&S.pstamp[0][0])[i] = 0u;
+  __syncthreads();
+  for (int32_t t = warp; t < p.n_tiles; t += KLF_WARPS) klf_tile_rescan<ASC, GBITS>(p, bits, t, keys);
+  __syncthreads();
+  // group keys of every group
+  auto group_fold = [&](int32_t g) {
+    const int32_t t = g * KL_GROUP + lane;
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    if (t < p.n_tiles) { k0 = keys[2 * t]; k1 = keys[2 * t + 1]; }
+    k0 = warp_max_u64(k0);
+    k1 = warp_max_u64(k1);
+    if (lane == 0) { gkeys[2 * g] = k0; gkeys[2 * g + 1] = k1; }
+  };
+  for (int32_t g = warp; g < n_groups; g += KLF_WARPS) group_fold(g);
+  __syncthreads();
+#define KLF_FINE(i) do { if (p.clocks && tid == 0) { const long long t_ = clock64(); S.fine[i] += t_ - S.fprev; S.fprev = t_; } } while (0)
+  uint32_t it_local = 0;
+  const unsigned lt = (1u << lane) - 1u;
+  (void)lt;
+  while (true) {
+    // ---- S1: every warp folds the group keys (identical result in every warp, no barrier) ----
+    if (S.done) break;
+    unsigned long long k0 = 0ull, k1 = 0ull;
+    for (int32_t g = lane; g < n_groups; g += 32) {
+      const unsigned long long a0 = gkeys[2 * g], a1 = gkeys[2 * g + 1];
+      k0 = a0 > k0 ? a0 : k0;
+      k1 = a1 > k1 ? a1 : k1;
+    }
+    const unsigned long long b0 = warp_max_u64(k0), b1 = warp_max_u64(k1);
+    if (b0 == 0ull || b1 == 0ull) break;               // no selectable node on one side (cKL.cpp:387-389)
+    KLF_FINE(0);
+    ++it_local;
+    const uint32_t stamp = it_local;
+    const int par = (int)(stamp & 1u);
+    const uint32_t ia = 0xFFFFFFFFu - (uint32_t)(b0 & 0xFFFFFFFFull), ib = 0xFFFFFFFFu - (uint32_t)(b1 & 0xFFFFFFFFull);
+    const int32_t a = ASC ? (int32_t)ia : __ldg(p.order0 + ia);
+    const int32_t b = ASC ? (int32_t)ib : __ldg(p.order1 + ib);
+    const int32_t ta = a / KL_TILE, tb = b / KL_TILE;
+    // ---- early rescan loads: the tiles of a and b (warps 14 and 15), before anything else is in flight ----
+    float ev[KL_TILE / 32];
+    uint32_t eid[KL_TILE / 32];
+    unsigned esg[KL_TILE / 32];
+    const bool early = (warp == KLF_ROW_WARPS - 2) || (warp == KLF_ROW_WARPS - 1 && tb != ta);
+    const int32_t et = (warp == KLF_ROW_WARPS - 2) ? ta : tb;
+    if (early) {
+#pragma unroll
+      for (int r = 0; r < KL_TILE / 32; ++r) {
+        const int32_t u = et * KL_TILE + r * 32 + lane;
+        ev[r] = u < p.n ? __ldcg(p.val + u) : 0.0f;
+        eid[r] = ASC ? (uint32_t)u : (u < p.n ? __ldg(p.rank + u) : 0u);
+        esg[r] = (GBITS && u < p.n) ? ((unsigned)__ldcg(p.state + u) & 3u) : ST_LOCK;
+      }
+    }
+    const int32_t alo = __ldg(p.rowptr + a), ahi = __ldg(p.rowptr + a + 1);
+    const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
+    const int32_t da = ahi - alo, items = da + (bhi - blo);
+    KLF_FINE(1);
+    KlfCtx X;
+    X.keys = keys; X.gkeys = gkeys; X.stamps = stamps; X.S = &S; X.val = p.val;
+    X.a = a; X.b = b; X.ta = ta; X.tb = tb; X.stamp = stamp; X.par = par;
+    if (warp == KLF_WARPS - 1) {
+      // ---- S2, concurrently with S3: gain, cut, trace, termination, lock-and-swap (the row warps take the sides of a
+      //      and b from (a, b) themselves, never from the words updated here) ----
+      float wab = 0.0f;
+      for (int32_t i = alo + lane; i < ahi; i += 32)
+        if (__ldg(p.col + i) == b) wab = __ldg(p.w + i);                                     // getEdgeWeight, cKL.cpp:75-82
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wab = fmaxf(wab, __shfl_xor_sync(FULL_MASK, wab, o));   // weights are > 0
+      if (lane == 0) {
+        const float maxGain = float_from_orderable((uint32_t)(b0 >> 32));
+        const float minGain = __fsub_rn(0.0f, float_from_orderable((uint32_t)(b1 >> 32)));
+        const float gain = __fsub_rn(__fsub_rn(maxGain, minGain), __fmul_rn(2.0f, wab));      // cKL.cpp:360
+        const float cut = __fsub_rn(S.cut, gain);                                            // cKL.cpp:362
+        S.cut = cut; S.iter = it_local;
+        p.t_cut[it_local] = cut; p.t_gain[it_local] = gain; p.t_n1[it_local] = a; p.t_n2[it_local] = b;
+        if (gain <= 0.0f) { if (++S.term > p.term_limit) S.done = 1; }                       // cKL.cpp:382-386
+        else S.term = 0;
+      } else if (lane == 1) {
+        __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));                                   // swip, cKL.cpp:274-286
+        if (!GBITS) bits[a >> 4] = (bits[a >> 4] & ~(3u << ((a & 15) * 2))) | ((ST_SIDE | ST_LOCK) << ((a & 15) * 2));
+        if (--S.rem0 == 0) S.done = 1;
+      } else if (lane == 2) {
+        __stcg(p.state + b, (uint8_t)(ST_LOCK));
+        if (--S.rem1 == 0) S.done = 1;
+        S.nlist[par ^ 1] = 0; S.ndirty[par ^ 1] = 0;               // the next swap's lists (nobody touches them now)
+      }
+      __syncwarp();
+      if (!GBITS && lane == 2) {                                    // after lane 1's word update (a and b may share a word)
+        bits[b >> 4] = (bits[b >> 4] & ~(3u << ((b & 15) * 2))) | (ST_LOCK << ((b & 15) * 2));
+      }
+    } else if (items <= KLF_MAXN) {
+      // ---- S3, flat: this thread's item, its neighbour's row extent ----
+      const int32_t it = lane * KLF_ROW_WARPS + warp;
+      int32_t my_v = 0, my_lo = 0, my_len = 0;
+      uint32_t my_id = 0u;
+      if (it < items) {
+        const int32_t e = it < da ? alo + it : blo + (it - da);
+        my_v = __ldg(p.col + e);
+        const int2 ext = __ldg(p.nb + e);
+        my_lo = ext.x; my_len = ext.y - ext.x;
+        my_id = ASC ? (uint32_t)my_v : __ldg(p.rank + my_v);
+      }
+      // rows of this warp: lanes 0 .. cnt-1
+      const int cnt = items > warp ? (items - 1 - warp) / KLF_ROW_WARPS + 1 : 0;
+      int inc = my_len;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int t = __shfl_up_sync(FULL_MASK, inc, d);
+        if (lane >= d) inc += t;
+      }
+      const int total = __shfl_sync(FULL_MASK, inc, 31);
+      const int my_off = inc - my_len;
+      KLF_FINE(2);
+      float *stg = S.stage[warp];
+      unsigned my_st = ST_LOCK;
+      float nv = 0.0f;
+      if (cnt > 0 && total <= KLF_WCAP) {
+        if (GBITS) { if (lane < cnt) my_st = (unsigned)__ldcg(p.state + my_v) & 3u; }
+        else if (lane < cnt) my_st = bits_get(bits, my_v);
+        // every 32-entry chunk of every row of the warp is a load slot; eight slots in flight per round (a warp
+        // owns 2-3 rows of ~20 entries on the circuits: one round, one L2 round trip)
+        constexpr int SLOTS = 8;
+        int j = 0, kk = 0;                                             // current row / offset inside it (warp-uniform)
+        while (j < cnt) {
+          int32_t s_lo[SLOTS], s_n[SLOTS], s_of[SLOTS];
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            s_n[s] = 0; s_lo[s] = 0; s_of[s] = 0;
+            if (j < cnt) {
+              const int len = __shfl_sync(FULL_MASK, my_len, j);
+              s_lo[s] = __shfl_sync(FULL_MASK, my_lo, j) + kk;
+              s_of[s] = __shfl_sync(FULL_MASK, my_off, j) + kk;
+              s_n[s] = min(32, len - kk);
+              kk += 32;
+              if (kk >= len) { ++j; kk = 0; }
+            }
+          }
+          int32_t c[SLOTS];
+          float ww[SLOTS];
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            c[s] = -1; ww[s] = 0.0f;
+            if (lane < s_n[s]) { c[s] = __ldg(p.col + s_lo[s] + lane); ww[s] = __ldg(p.w + s_lo[s] + lane); }
+          }
+          unsigned sd[SLOTS];
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s) {
+            sd[s] = 0u;
+            if (c[s] >= 0) {
+              if (c[s] == a) sd[s] = 1u;                                 // the pair being swapped: sides after the swap
+              else if (c[s] == b) sd[s] = 0u;
+              else sd[s] = GBITS ? ((unsigned)__ldcg(p.state + c[s]) & ST_SIDE) : (bits_get(bits, c[s]) & ST_SIDE);
+            }
+          }
+#pragma unroll
+          for (int s = 0; s < SLOTS; ++s)
+            if (c[s] >= 0) stg[s_of[s] + lane] = sd[s] ? ww[s] : -ww[s];
+        }
+        __syncwarp();
+        KLF_FINE(3);
+        if (lane < cnt) {
+          // the two ordered sums of cKL.cpp:225-251: E over the external weights, I over the internal ones, row order
+          float E = 0.0f, I = 0.0f;
+          const float *src = stg + my_off;
+          for (int t = 0; t < my_len; ++t) {
+            const float x = src[t];
+            E = __fadd_rn(E, fmaxf(x, 0.0f));
+            I = __fadd_rn(I, fmaxf(-x, 0.0f));
+          }
+          nv = __fsub_rn(E, I);
+          klf_publish<ASC>(X, my_v, my_id, my_st, nv);
+        }
+        KLF_FINE(4);
+      } else if (cnt > 0) {
+        // the warp's rows do not fit its slice (a hub row): warp-per-row replay, one row after the other
+        for (int j = 0; j < cnt; ++j) {
+          const int32_t v = __shfl_sync(FULL_MASK, my_v, j);
+          const uint32_t vid = __shfl_sync(FULL_MASK, my_id, j);
+          const int32_t lo = __shfl_sync(FULL_MASK, my_lo, j), hi = lo + __shfl_sync(FULL_MASK, my_len, j);
+          klf_row_replay<ASC, GBITS>(p, X, bits, v, vid, lo, hi, stg);
+        }
+      }
+    } else {
+      // ---- more neighbours than threads (industry2-class hubs): warp-per-row over the whole list ----
+      float *stg = S.stage[warp];
+      for (int32_t it = warp; it < items; it += KLF_ROW_WARPS) {
+        const int32_t e = it < da ? alo + it : blo + (it - da);
+        const int32_t v = __ldg(p.col + e);
+        const int2 ext = __ldg(p.nb + e);
+        const uint32_t vid = ASC ? (uint32_t)v : __ldg(p.rank + v);
+        klf_row_replay<ASC, GBITS>(p, X, bits, v, vid, ext.x, ext.y, stg);
+      }
+    }
+    KLF_FINE(5);
+    __syncthreads();                                   // (A) every D-value, patch, raise and rescan request of this swap is in
+    KLF_FINE(6);
+    // ---- S4: rescans.  Early tiles from the values loaded at the top, patched; late tiles with one round trip ----
+    const int nl = S.nlist[par];
+    if (early) {
+      unsigned long long e0 = 0ull, e1 = 0ull;
+      const int s = (warp == KLF_ROW_WARPS - 2) ? 0 : 1;
+#pragma unroll
+      for (int r = 0; r < KL_TILE / 32; ++r) {
+        const int idx = r * 32 + lane;
+        const int32_t u = et * KL_TILE + idx;
+        if (u >= p.n || u == a || u == b) continue;
+        const unsigned st = GBITS ? esg[r] : bits_get(bits, u);
+        if (st & ST_LOCK) continue;
+        const float x = (S.pstamp[s][idx] == stamp) ? S.patch[s][idx] : ev[r];
+        const unsigned long long key = kl_key<ASC>(x, st & ST_SIDE, eid[r]);
+        if (st & ST_SIDE) e1 = key > e1 ? key : e1; else e0 = key > e0 ? key : e0;
+      }
+      e0 = warp_max_u64(e0);
+      e1 = warp_max_u64(e1);
+      if (lane == 0) {
+        keys[2 * et] = e0; keys[2 * et + 1] = e1;
+        const int32_t g = et / KL_GROUP;
+        if (atomicExch(gstamp + g, stamp) != stamp) S.dlist[par][atomicAdd(&S.ndirty[par], 1)] = g;
+      }
+    } else if (warp < KLF_ROW_WARPS - 2) {
+      for (int q = warp; q < nl; q += KLF_ROW_WARPS - 2) {
+        const int32_t t = S.list[par][q];
+        klf_tile_rescan<ASC, GBITS>(p, bits, t, keys);
+        if (lane == 0) {
+          const int32_t g = t / KL_GROUP;
+          if (atomicExch(gstamp + g, stamp) != stamp) S.dlist[par][atomicAdd(&S.ndirty[par], 1)] = g;
+        }
+      }
+    }
+    if (p.clocks && tid == 0) S.fine[14] += nl;
+    KLF_FINE(7);
+    __syncthreads();                                   // (B) tile keys final
+    KLF_FINE(8);
+    {
+      const int nd = S.ndirty[par];
+      for (int q = warp; q < nd; q += KLF_WARPS) group_fold(S.dlist[par][q]);
+    }
+    __syncthreads();                                   // (C) group keys final
+    KLF_FINE(9);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    p.ctrl[0] = (int64_t)S.iter; p.ctrl[1] = 1;
+    if (p.clocks)
+      for (int i = 0; i < 16; ++i) p.ctrl[16 + i] = S.fine[i];
+  }
+#undef KLF_FINE
 }
 
 // Best-prefix rollback (the classic KL pass ends by keeping only the swaps up to the best cut -- the
@@ -1040,6 +1525,7 @@ void kl_run(eigkl_handle *h) {
   // state in shared memory (one CTA) whenever it fits, unless a cluster size was asked for explicitly
   const bool local = R == 1 && h->kl_local && h->opts.kl_cluster <= 0 && n <= KL_LOCAL_GBITS_MAX_N;
   const bool gbits = local && (n > KL_LOCAL_MAX_N || getenv("EIGKL_KL_GBITS") != nullptr);
+  const bool flat = local && h->kl_flat;
   if (!local) {
     tile_init_kernel<<<grid_for((int64_t)n_tiles * 32), TPB, 0, st>>>(k.state.p, k.val.p, k.rank.p, own_lo, own_hi, n_tiles, k.tile_key.p, k.tile_stamp.p);
     h->launches++;
@@ -1054,7 +1540,7 @@ void kl_run(eigkl_handle *h) {
   EIGKL_CUDA(cudaMemcpyAsync(k.t_gain.p, &zero, sizeof(float), cudaMemcpyHostToDevice, st));
   EIGKL_CUDA(cudaMemcpyAsync(k.t_n1.p, &neg, sizeof(int32_t), cudaMemcpyHostToDevice, st));
   EIGKL_CUDA(cudaMemcpyAsync(k.t_n2.p, &neg, sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  EIGKL_CUDA(cudaMemsetAsync(k.ctrl.p, 0, 2 * sizeof(int64_t), st));
+  EIGKL_CUDA(cudaMemsetAsync(k.ctrl.p, 0, 4 * sizeof(int64_t), st));
   h->timer.stop(st);
   h->stats.ms_kl_setup = h->timer.ms();
 
@@ -1111,7 +1597,27 @@ void kl_run(eigkl_handle *h) {
       h->attr_kl_local = true;
     }
     nc = 1;
-    if (k.ascending) {
+    if (flat) {
+      const size_t n_groups = (size_t)ceil_div(n_tiles, KL_GROUP);
+      const size_t fsmem = (size_t)n_tiles * 20 + n_groups * 20 + sizeof(KlFlatSmem) + (gbits ? 0 : (size_t)((n + 15) / 16) * 4) + 16;
+      if (!h->attr_kl_flat) {
+        const size_t lim = 227 * 1024;
+        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
+        h->attr_kl_flat = true;
+      }
+      EIGKL_REQUIRE(fsmem <= 227 * 1024, EIGKL_E_ARG, "KL flat loop: shared-memory plan exceeds the SM");
+      const unsigned fgrid = 1;       // (147 sleeping "company" CTAs were tried against the lone-CTA issue throttle: no effect)
+      if (k.ascending) {
+        if (gbits) kl_loop_flat_kernel<true, true><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
+        else kl_loop_flat_kernel<true, false><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
+      } else {
+        if (gbits) kl_loop_flat_kernel<false, true><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
+        else kl_loop_flat_kernel<false, false><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
+      }
+    } else if (k.ascending) {
       if (gbits) kl_loop_local_kernel<true, true><<<1, KL_LOOP_THREADS, smem, st>>>(q);
       else kl_loop_local_kernel<true, false><<<1, KL_LOOP_THREADS, smem, st>>>(q);
     } else {
@@ -1149,7 +1655,7 @@ void kl_run(eigkl_handle *h) {
     }
   }
   h->timer.stop(st);
-  int64_t ctrl[16] = {0};
+  int64_t ctrl[32] = {0};
   EIGKL_CUDA(cudaMemcpyAsync(ctrl, k.ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
   EIGKL_CUDA(cudaStreamSynchronize(st));
   EIGKL_CUDA(cudaGetLastError());
@@ -1163,10 +1669,26 @@ void kl_run(eigkl_handle *h) {
     fprintf(stderr, "[eigkl] KL phases, cycles per swap (thread 0):");
     for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f;", nm[i], (double)ctrl[8 + i] / (double)k.swaps);
     fprintf(stderr, "\n");
+    if (local && flat) {
+      static const char *fn[10] = {"S1 group fold", "decode+rowptr (+early loads issued)", "nbr entries arrive + scan", "rows staged", "row sums + publish",
+                                   "S3 tail", "barrier A", "rescans", "barrier B", "group refold + barrier C"};
+      fprintf(stderr, "[eigkl] KL flat-loop probes, cycles per swap (thread 0):");
+      for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %.0f;", fn[i], (double)ctrl[16 + i] / (double)k.swaps);
+      fprintf(stderr, " late rescans per swap %.2f\n", (double)ctrl[16 + 14] / (double)k.swaps);
+    } else if (local) {
+      static const char *fn[13] = {"S1 local max", "S1 barrier 1", "S1 final max", "S1 barrier 2", "decode+rowptr", "nbr entries arrive",
+                                   "row loads arrive (per batch)", "row sums (all rows)", "row epilogues (all rows)", "S3 tail", "S3 barrier",
+                                   "S4 rescans", "S4 barrier"};
+      fprintf(stderr, "[eigkl] KL fine probes, cycles per swap (thread 0):");
+      for (int i = 0; i < 13; ++i) fprintf(stderr, " %s %.0f;", fn[i], (double)ctrl[16 + i] / (double)k.swaps);
+      fprintf(stderr, " tiles rescanned per swap %.2f\n", (double)ctrl[16 + 14] / (double)k.swaps);
+    }
   }
   h->stats.kl_cluster = nc;
   h->stats.kl_threads = nc * KL_LOOP_THREADS;
   h->stats.kl_local = local ? (gbits ? 2 : 1) : 0;
+  h->stats.kl_flat = flat ? 1 : 0;
+  h->stats.kl_threads = flat ? KLF_THREADS : nc * KL_LOOP_THREADS;
 }
 
 }  // namespace eigkl

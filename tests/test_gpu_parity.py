@@ -120,13 +120,16 @@ def test_kl_trace_byte_exact_vs_reference(c, handles, workdir, tmp_path):
 
 
 @pytest.mark.parametrize("c", CIRCUITS)
-@pytest.mark.parametrize("variant", ["shared_bits", "global_bits", "global_state"])
+@pytest.mark.parametrize("variant", ["shared_bits", "global_bits", "warp_shared_bits", "warp_global_bits", "global_state"])
 def test_kl_loop_variants_byte_exact(c, variant, circuits, workdir, tmp_path, monkeypatch):
-    """The three single-GPU swap loops -- tile keys + side bits in shared memory (default up to 524 288 nodes), tile
-    keys in shared memory with the state bytes in global memory (up to 2 M nodes), everything in global memory (the
-    cluster kernel) -- all reproduce the reference's one-core trace byte for byte."""
-    if variant == "global_bits":
+    """The single-GPU swap loops -- tile keys + side bits in shared memory (default up to 524 288 nodes), tile keys in
+    shared memory with the state bytes in global memory (up to 2 M nodes), each in its flat (default: a lane per
+    neighbour row) and warp-per-row form, and everything in global memory (the cluster kernel) -- all reproduce the
+    reference's one-core trace byte for byte."""
+    if variant.endswith("global_bits"):
         monkeypatch.setenv("EIGKL_KL_GBITS", "1")
+    if variant.startswith("warp_"):
+        monkeypatch.setenv("EIGKL_KL_FLAT", "0")
     if variant == "global_state":
         monkeypatch.setenv("EIGKL_KL_LOCAL", "0")
     with api.Handle() as h:
@@ -134,7 +137,9 @@ def test_kl_loop_variants_byte_exact(c, variant, circuits, workdir, tmp_path, mo
         h.assemble_kl_graph()
         h.load_eig(datasets.golden_eig_path(workdir, c))
         tr = h.kl_run()
-        assert h.stats()["kl_local"] == {"shared_bits": 1, "global_bits": 2, "global_state": 0}[variant]
+        st = h.stats()
+        assert st["kl_local"] == {"shared_bits": 1, "global_bits": 2, "warp_shared_bits": 1, "warp_global_bits": 2, "global_state": 0}[variant]
+        assert st["kl_flat"] == (1 if variant in ("shared_bits", "global_bits") else 0)
     out = str(tmp_path / "trace.txt")
     api.write_trace(out, tr)
     raw = open(out, "rb").read()
