@@ -535,8 +535,24 @@ int eigkl_time_kernel(eigkl_handle *h, int what, int iters, int flush_l2, double
     cudaEvent_t a, b;
     EIGKL_CUDA(cudaEventCreate(&a)); EIGKL_CUDA(cudaEventCreate(&b));
     double total = 0.0;
+    // row-partitioned: a chain of SpMVs through the three exchange buffers, each pushing its export rows to the peers
+    // from its epilogue and waiting for the peers' halo of its input -- the chain a filter application runs
+    // (collective: every rank calls with the same arguments)
+    const bool dist = what == 0 && h->dist.valid;
+    int cur = 0;
+    uint32_t have = 0;
+    if (dist) {
+      for (int b = 0; b < 3; ++b) EIGKL_CUDA(cudaMemsetAsync(dist_own(h, b), 0, (size_t)h->dist.n_pad * sizeof(double), h->stream));
+      have = dist_push(h, 0);
+    }
     auto launch = [&] {
-      if (what == 0) spmv_launch(h, x.p, y.p, nullptr, nullptr);
+      if (dist) {
+        const int out = (cur + 1) % 3;
+        SpmvDist d{have, ++h->arena.seq, out};
+        spmv_launch_ex(h, dist_buf(h, cur), dist_own(h, cur), nullptr, dist_own(h, out), nullptr, nullptr, 1.0, 0.0, 0.0, &d);
+        have = d.push_seq;
+        cur = out;
+      } else if (what == 0) spmv_launch(h, x.p, y.p, nullptr, nullptr);
       else kl_dvalues(h);
     };
     launch(); launch();                                     // warm-up
@@ -564,6 +580,7 @@ int eigkl_time_kernel(eigkl_handle *h, int what, int iters, int flush_l2, double
     }
     cudaEventDestroy(a); cudaEventDestroy(b);
     h->prof.on = prof;
+    if (dist) dist_check(h);
     *ms_avg = total / iters;
   });
 }

@@ -319,7 +319,8 @@ struct eigkl_handle {
   int spmv_resident = 1;       // EIGKL_SPMV_RESIDENT=0: one launch per SpMV even when the matrix fits on chip
   int gs_fused = 1;            // EIGKL_GS_FUSED=0: Gram-Schmidt as separate multidot / update launches
   // per-handle (= per-device) one-time kernel attribute set-up, and what the device allows
-  bool attr_kl_local = false, attr_kl_flat = false, attr_gs = false, attr_resident = false;
+  bool attr_kl_local = false, attr_gs = false, attr_resident = false;
+  unsigned attr_kl_flat = 0;   // one bit per variant of the flat KL loop whose shared-memory limit has been raised
   int coop_ok = -1;            // -1 unknown, 0/1: cudaDevAttrCooperativeLaunch
   int kl_local = 1;            // EIGKL_KL_LOCAL=0: never run the swap loop with its state in shared memory
   int kl_flat = 1;             // EIGKL_KL_FLAT=0: the warp-per-row form of the shared-memory swap loop (kl_loop_local_kernel)

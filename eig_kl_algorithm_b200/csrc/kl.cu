@@ -283,7 +283,7 @@ static void kl_alloc_state(eigkl_handle *h, int32_t n) {
   const int64_t n_tiles = ceil_div(n, KL_TILE);
   k.tile_key.ensure((size_t)(2 * n_tiles + 2 * KL_MAX_CLUSTER + 8));
   k.tile_stamp.ensure((size_t)n_tiles + 1);
-  k.ctrl.ensure(40);
+  k.ctrl.ensure(64);
 }
 
 void kl_set_partition_device(eigkl_handle *h, const uint8_t *side_dev) {
@@ -1099,40 +1099,56 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
 }
 
 // ---------------------------------------------------------------------------------------------------
-// The swap loop, third form ("flat"): the same state in shared memory as kl_loop_local_kernel, restructured after
-// its phase clocks (ibm10, cycles per swap of ~9 400: S1 1 500; row pointers 730; neighbour entries 830; neighbour
-// rows 1 000; the two ordered row sums of the slowest warp 2 200 + 730 of epilogue; tile rescans 1 800 behind a
-// barrier; every dependent global load costs 700-1 000 cycles from a lone CTA, not the 250 of an L2 hit):
-//   * 512 threads.  Item i of N(a) ++ N(b) belongs to lane i/15 of warp i%15, so a warp OWNS its rows: it loads
-//     their entries (all rows and all 32-entry chunks in flight at once), stages the signed weights in its private
-//     slice of shared memory
-//     and then every lane adds ITS row serially -- the fp32 order of cKL.cpp:225-251 -- with all rows of the block
-//     summed concurrently (~20 dependent FADD pairs) instead of one row per warp at a time.  No block barrier
-//     inside the phase; a warp whose rows exceed its slice falls back to the warp-per-row replay.
-//   * pair selection is two-level: keys per 256-node tile and per group of 32 tiles; EVERY warp folds the group
-//     keys itself (no broadcast barrier), a raised key raises its group in place, and only groups whose tiles were
-//     rescanned are recomputed.
-//   * the tiles of a and b always need a rescan (their best nodes were just locked): their D-values are loaded
-//     at the START of the swap by two otherwise idle warps and patched after the row sums with the values
-//     recomputed in this swap (a 256-entry patch slice per tile), so that rescan costs no round trip of its own.
-//   * a neighbour that holds its tile's best key forces a rescan only when its key went DOWN; a raised holder is
-//     updated in place.
-// The arithmetic is untouched: traces stay byte-identical (test_kl_loop_variants_byte_exact).
+// The swap loop, third form ("flat"): the same state in shared memory as kl_loop_local_kernel, laid out by ENTRY.
+// ncu on the earlier forms (profiles/r02_kl_flat_ibm10.md): the loop is not waiting for memory -- an L2 hit is 282
+// cycles from a lone CTA (tools/micro/chase.cu) and the four dependent trips of a swap explain ~1 100 of its
+// ~10 000 cycles -- it is issue- and barrier-bound: 14 800 warp instructions per swap, a third of them the per-warp
+// slot bookkeeping that spread ~40 neighbour rows over 15 warps, and a third of all warp cycles spent waiting at
+// block barriers for the slowest warp (the 256-entry rescans of the two winners' tiles, the group refolds).
+// This form does the least work per swap that the arithmetic allows:
+//   * ITEMS: the neighbour list N(a) ++ N(b), one item per thread, dense from thread 0 (ibm10: 41 items = 2
+//     warps).  One load gives (v, rowptr[v], rowptr[v+1]); a warp scan + the warps' totals give every row's
+//     offset in ONE flat list of entries.
+//   * ENTRIES: thread g handles flat entry g (and g + 416, ...): a 4-step search over the warp totals (shuffles)
+//     and a 5-step search over its warp's offsets (shared memory) name the row, then ONE coalesced round of loads
+//     (col, w), the side bit from shared memory, and the signed weight goes to stage[g].  No per-row loops, no
+//     slots: ~60 instructions per thread whatever the row lengths.
+//   * SUMS: the item's thread adds its row's segment of stage[] serially -- the fp32 order of cKL.cpp:225-251 --
+//     all rows concurrently, and publishes the D-value (tile key raised in place, late rescan only when the
+//     holder of a tile's best key lost ground).
+//   * the tiles of a and b always need new keys (their best nodes were just locked).  Two otherwise idle warps
+//     load those tiles' D-values at the START of the swap and reduce them to a base key per side, leaving out
+//     the nodes this swap recomputes (an exclusion bitmap the item threads fill); recomputed nodes of those
+//     tiles go to a per-tile key by atomicMax.  After the barrier the tile's key is max(base, published): two
+//     shared-memory words instead of a 256-entry rescan behind the barrier.
+//   * the same two warps then refold the groups of those tiles; when no late rescan was requested (9 swaps in
+//     10) that is the whole epilogue: one barrier instead of three.
+// Hub swaps (more neighbours than row threads, or more entries than the staging buffer) take the warp-per-row
+// replay.  The arithmetic is untouched: traces stay byte-identical (test_kl_loop_variants_byte_exact).
 // ---------------------------------------------------------------------------------------------------
 constexpr int KLF_THREADS = 512;
 constexpr int KLF_WARPS = KLF_THREADS / 32;
-constexpr int KLF_ROW_WARPS = KLF_WARPS - 1;   // warps that own neighbour rows; the last warp keeps the books
-constexpr int KLF_MAXN = KLF_ROW_WARPS * 32;   // |N(a)| + |N(b)| handled on the flat path
-constexpr int KLF_WCAP = 384;                  // staged entries per warp
-constexpr int KLF_LCAP = KLF_MAXN + 8;         // late rescans / dirty groups per swap
-constexpr int KL_GROUP = 32;                   // tiles per group key
+constexpr int KLF_ROW_WARPS = 13;               // warps 0..12: items, entries, sums
+constexpr int KLF_E0 = 13, KLF_E1 = 14;         // the early-tile warps (tile of a, tile of b)
+constexpr int KLF_BK = 15;                      // the bookkeeper
+constexpr int KLF_ROW_THREADS = KLF_ROW_WARPS * 32;
+constexpr int KLF_MAXN = KLF_ROW_THREADS;       // |N(a)| + |N(b)| handled on the flat path
+constexpr int KLF_ENT = 4096;                   // staged entries per swap
+constexpr int KLF_LCAP = KLF_MAXN + 8;          // late rescans / dirty groups per swap
+constexpr int KL_GROUP = 32;                    // tiles per group key
 
-struct KlFlatSmem {                            // fixed part, placed after the size-dependent arrays
-  float stage[KLF_WARPS][KLF_WCAP];
-  float patch[2][KL_TILE];
-  uint32_t pstamp[2][KL_TILE];
-  int32_t list[2][KLF_LCAP];      // late rescans of a swap, double-buffered by the swap's parity: the counters of the
-  int32_t dlist[2][KLF_LCAP];     // NEXT swap are cleared while this swap's lists are still being read
+struct KlFlatSmem {                             // fixed part, placed after the size-dependent arrays
+  float stage[KLF_ENT];
+  int32_t it_lo[KLF_ROW_THREADS + 1];           // first entry of the item's row
+  int32_t it_len[KLF_ROW_THREADS + 1];          // its length
+  int32_t it_inc[KLF_ROW_THREADS];              // inclusive prefix of the row lengths inside the item's warp
+  unsigned long long best[2];                   // the pair selection of the NEXT swap when best_stamp names this one
+  uint32_t best_stamp;
+  int32_t wtot[16];                             // entries of the items of each row warp
+  unsigned long long pkey[2][2][2];             // [swap parity][tile of a / tile of b][side]: best published key
+  uint32_t excl[2][2][KL_TILE / 32];            // [swap parity][tile of a / b]: nodes recomputed in this swap
+  int32_t list[2][KLF_LCAP];                    // late rescans of a swap, double-buffered by the swap's parity: the counters
+  int32_t dlist[2][KLF_LCAP + 8];               // of the NEXT swap are cleared while this swap's lists are still being read
   float wab;
   float cut;
   uint32_t term, iter;
@@ -1142,9 +1158,6 @@ struct KlFlatSmem {                            // fixed part, placed after the s
   long long fprev;
 };
 
-// What is not on the common path of a swap -- the warp-per-row replay for hub rows, the late tile rescans -- is an
-// out-of-line function with one body shared by its call sites (the loop body is ~30 KB of code as it is).  The
-// update of a node's tile key is on the common path and stays inline (out of line it measured 12 % slower).
 struct KlfCtx {
   unsigned long long *keys, *gkeys;
   uint32_t *stamps;
@@ -1154,24 +1167,27 @@ struct KlfCtx {
   uint32_t stamp;
   int par;
 };
+__device__ __forceinline__ uint32_t *key_lo(unsigned long long *k) { return reinterpret_cast<uint32_t *>(k); }       // ~position
+__device__ __forceinline__ uint32_t *key_hi(unsigned long long *k) { return reinterpret_cast<uint32_t *>(k) + 1; }   // orderable(D)
 template <bool ASC>
 __device__ __forceinline__ void klf_publish(const KlfCtx &X, int32_t v, uint32_t vid, unsigned st, float nv) {
   __stcg(X.val + v, nv);
   if ((st & ST_LOCK) || v == X.a || v == X.b) return;
   const int32_t tile = v / KL_TILE;
   KlFlatSmem &S = *X.S;
-  if (tile == X.ta || tile == X.tb) {                 // the early rescan of that tile takes the new value from here
-    const int s = (tile == X.ta) ? 0 : 1;
-    S.patch[s][v % KL_TILE] = nv;
-    S.pstamp[s][v % KL_TILE] = X.stamp;
+  const unsigned long long nk = kl_key<ASC>(nv, st & ST_SIDE, vid);
+  if (tile == X.ta || tile == X.tb) {                 // the early warp of that tile folds this in after the barrier
+    atomicMax(&S.pkey[X.par][tile == X.ta ? 0 : 1][st & ST_SIDE], nk);
     return;
   }
   unsigned long long *kp = X.keys + 2 * tile + (st & ST_SIDE);
-  const unsigned long long nk = kl_key<ASC>(nv, st & ST_SIDE, vid);
   const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
   if (cur != 0ull && (uint32_t)(cur & 0xFFFFFFFFull) == 0xFFFFFFFFu - vid && nk < cur) {
     // v held the tile's best key and lost ground: the tile is rescanned
-    if (atomicExch(X.stamps + tile, X.stamp) != X.stamp) S.list[X.par][atomicAdd(&S.nlist[X.par], 1)] = tile;
+    if (atomicExch(X.stamps + tile, X.stamp) != X.stamp) {
+      const int slot = atomicAdd(&S.nlist[X.par], 1);
+      if (slot < KLF_LCAP) S.list[X.par][slot] = tile;            // beyond the list (a hub swap): every tile is rescanned
+    }
   } else if (atomicMax(kp, nk) < nk) {
     atomicMax(X.gkeys + 2 * (tile / KL_GROUP) + (st & ST_SIDE), nk);
   }
@@ -1190,8 +1206,12 @@ template <bool ASC, bool GBITS>
 __device__ __noinline__ void klf_tile_rescan(const KlLocalParams &p, const uint32_t *bits, int32_t tile, unsigned long long *keys) {
   tile_scan_local<ASC, GBITS>(bits, p.state, p.val, p.rank, p.n, tile, threadIdx.x & 31, keys);
 }
+__device__ __forceinline__ void klf_bar_items() { asm volatile("bar.sync 1, %0;" ::"n"((KLF_ROW_WARPS + 2) * 32) : "memory"); }   // row + early warps
+__device__ __forceinline__ void klf_bar_rows() { asm volatile("bar.sync 2, %0;" ::"n"(KLF_ROW_WARPS * 32) : "memory"); }          // row warps
+__device__ __forceinline__ void klf_bar_early_arrive() { __threadfence_block(); asm volatile("bar.arrive 3, 64;" ::: "memory"); }
+__device__ __forceinline__ void klf_bar_early_sync() { asm volatile("bar.sync 3, 64;" ::: "memory"); }
 
-template <bool ASC, bool GBITS>
+template <bool ASC, bool GBITS, bool CLOCKS>
 __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLocalParams p) {
   extern __shared__ __align__(16) unsigned char kl_sm[];
   const int32_t n_groups = (p.n_tiles + KL_GROUP - 1) / KL_GROUP;
@@ -1222,7 +1242,10 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
   }
   for (int32_t t = tid; t < p.n_tiles; t += KLF_THREADS) stamps[t] = 0u;
   for (int32_t g = tid; g < n_groups; g += KLF_THREADS) gstamp[g] = 0u;
-  for (int i = tid; i < 2 * KL_TILE; i += KLF_THREADS) (&S.pstamp[0][0])[i] = 0u;
+  if (tid < 8) (&S.pkey[0][0][0])[tid] = 0ull;
+  if (tid < 2 * 2 * (KL_TILE / 32)) (&S.excl[0][0][0])[tid] = 0u;
+  if (tid < 16) S.wtot[tid] = 0;
+  if (tid == 0) { S.best_stamp = 0xFFFFFFFFu; S.it_lo[KLF_ROW_THREADS] = 0; S.it_len[KLF_ROW_THREADS] = 0; }
   __syncthreads();
   for (int32_t t = warp; t < p.n_tiles; t += KLF_WARPS) klf_tile_rescan<ASC, GBITS>(p, bits, t, keys);
   __syncthreads();
@@ -1237,20 +1260,24 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
   };
   for (int32_t g = warp; g < n_groups; g += KLF_WARPS) group_fold(g);
   __syncthreads();
-#define KLF_FINE(i) do { if (p.clocks && tid == 0) { const long long t_ = clock64(); S.fine[i] += t_ - S.fprev; S.fprev = t_; } } while (0)
+#define KLF_FINE(i) do { if (CLOCKS && tid == 0) { const long long t_ = clock64(); S.fine[i] += t_ - S.fprev; S.fprev = t_; } } while (0)
   uint32_t it_local = 0;
-  const unsigned lt = (1u << lane) - 1u;
-  (void)lt;
   while (true) {
     // ---- S1: every warp folds the group keys (identical result in every warp, no barrier) ----
     if (S.done) break;
-    unsigned long long k0 = 0ull, k1 = 0ull;
-    for (int32_t g = lane; g < n_groups; g += 32) {
-      const unsigned long long a0 = gkeys[2 * g], a1 = gkeys[2 * g + 1];
-      k0 = a0 > k0 ? a0 : k0;
-      k1 = a1 > k1 ? a1 : k1;
+    unsigned long long b0, b1;
+    if (S.best_stamp == it_local) {                    // the warp that refolded the groups of the last swap left the answer
+      b0 = S.best[0]; b1 = S.best[1];
+    } else {
+      unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll 1
+      for (int32_t g = lane; g < n_groups; g += 32) {
+        const unsigned long long a0 = gkeys[2 * g], a1 = gkeys[2 * g + 1];
+        k0 = a0 > k0 ? a0 : k0;
+        k1 = a1 > k1 ? a1 : k1;
+      }
+      b0 = warp_max_u64(k0); b1 = warp_max_u64(k1);
     }
-    const unsigned long long b0 = warp_max_u64(k0), b1 = warp_max_u64(k1);
     if (b0 == 0ull || b1 == 0ull) break;               // no selectable node on one side (cKL.cpp:387-389)
     KLF_FINE(0);
     ++it_local;
@@ -1260,12 +1287,13 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
     const int32_t a = ASC ? (int32_t)ia : __ldg(p.order0 + ia);
     const int32_t b = ASC ? (int32_t)ib : __ldg(p.order1 + ib);
     const int32_t ta = a / KL_TILE, tb = b / KL_TILE;
-    // ---- early rescan loads: the tiles of a and b (warps 14 and 15), before anything else is in flight ----
+    // ---- early loads: the tiles of a and b (warps E0 / E1), before anything else is in flight ----
     float ev[KL_TILE / 32];
     uint32_t eid[KL_TILE / 32];
     unsigned esg[KL_TILE / 32];
-    const bool early = (warp == KLF_ROW_WARPS - 2) || (warp == KLF_ROW_WARPS - 1 && tb != ta);
-    const int32_t et = (warp == KLF_ROW_WARPS - 2) ? ta : tb;
+    const bool early = (warp == KLF_E0) || (warp == KLF_E1 && tb != ta);
+    const int32_t et = (warp == KLF_E1) ? tb : ta;
+    const int es = (warp == KLF_E1) ? 1 : 0;
     if (early) {
 #pragma unroll
       for (int r = 0; r < KL_TILE / 32; ++r) {
@@ -1279,10 +1307,13 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
     const int32_t blo = __ldg(p.rowptr + b), bhi = __ldg(p.rowptr + b + 1);
     const int32_t da = ahi - alo, items = da + (bhi - blo);
     KLF_FINE(1);
-    KlfCtx X;
-    X.keys = keys; X.gkeys = gkeys; X.stamps = stamps; X.S = &S; X.val = p.val;
-    X.a = a; X.b = b; X.ta = ta; X.tb = tb; X.stamp = stamp; X.par = par;
-    if (warp == KLF_WARPS - 1) {
+    // the context of the out-of-line hub routines is built only where they are called: it lives in local memory
+    auto make_ctx = [&](KlfCtx &X) {
+      X.keys = keys; X.gkeys = gkeys; X.stamps = stamps; X.S = &S; X.val = p.val;
+      X.a = a; X.b = b; X.ta = ta; X.tb = tb; X.stamp = stamp; X.par = par;
+    };
+    unsigned long long base0 = 0ull, base1 = 0ull;     // early warps: best keys of the tile's nodes this swap leaves alone
+    if (warp == KLF_BK) {
       // ---- S2, concurrently with S3: gain, cut, trace, termination, lock-and-swap (the row warps take the sides of a
       //      and b from (a, b) themselves, never from the words updated here) ----
       float wab = 0.0f;
@@ -1307,165 +1338,306 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
         __stcg(p.state + b, (uint8_t)(ST_LOCK));
         if (--S.rem1 == 0) S.done = 1;
         S.nlist[par ^ 1] = 0; S.ndirty[par ^ 1] = 0;               // the next swap's lists (nobody touches them now)
+      } else if (lane >= 4 && lane < 8) {
+        (&S.pkey[par ^ 1][0][0])[lane - 4] = 0ull;
+      } else if (lane >= 8 && lane < 8 + 2 * (KL_TILE / 32)) {
+        (&S.excl[par ^ 1][0][0])[lane - 8] = 0u;
       }
       __syncwarp();
       if (!GBITS && lane == 2) {                                    // after lane 1's word update (a and b may share a word)
         bits[b >> 4] = (bits[b >> 4] & ~(3u << ((b & 15) * 2))) | (ST_LOCK << ((b & 15) * 2));
       }
+    } else if (warp >= KLF_ROW_WARPS) {
+      // ---- the early warps: wait for the exclusion bitmap, fold the tile's untouched nodes into a base key per side ----
+      klf_bar_items();
+      if (early) {
+#pragma unroll
+        for (int r = 0; r < KL_TILE / 32; ++r) {
+          const int idx = r * 32 + lane;
+          const int32_t u = et * KL_TILE + idx;
+          if (u >= p.n || u == a || u == b) continue;
+          if ((S.excl[par][es][r] >> lane) & 1u) continue;          // recomputed in this swap: arrives through pkey
+          const unsigned st = GBITS ? esg[r] : bits_get(bits, u);
+          if (st & ST_LOCK) continue;
+          const unsigned long long key = kl_key<ASC>(ev[r], st & ST_SIDE, eid[r]);
+          if (st & ST_SIDE) base1 = key > base1 ? key : base1; else base0 = key > base0 ? key : base0;
+        }
+        base0 = warp_max_u64(base0);
+        base1 = warp_max_u64(base1);
+      }
     } else if (items <= KLF_MAXN) {
-      // ---- S3, flat: this thread's item, its neighbour's row extent ----
-      const int32_t it = lane * KLF_ROW_WARPS + warp;
-      int32_t my_v = 0, my_lo = 0, my_len = 0;
+      // ---- S3, flat.  ITEMS: this thread's neighbour, its row extent, the row's offset in the flat entry list ----
+      int32_t my_v = 0, my_len = 0;
       uint32_t my_id = 0u;
-      if (it < items) {
-        const int32_t e = it < da ? alo + it : blo + (it - da);
+      unsigned my_st = ST_LOCK;
+      int32_t my_lo = 0;
+      if (tid < items) {
+        const int32_t e = tid < da ? alo + tid : blo + (tid - da);
         my_v = __ldg(p.col + e);
         const int2 ext = __ldg(p.nb + e);
         my_lo = ext.x; my_len = ext.y - ext.x;
+        if (CLOCKS && my_len >= 0) KLF_FINE(11);
         my_id = ASC ? (uint32_t)my_v : __ldg(p.rank + my_v);
+        if (GBITS) my_st = (unsigned)__ldcg(p.state + my_v) & 3u;     // needed at the publish: in flight across the entry phase
+        const int32_t tv = my_v / KL_TILE;
+        if (tv == ta) atomicOr(&S.excl[par][0][(my_v % KL_TILE) >> 5], 1u << (my_v & 31));
+        else if (tv == tb) atomicOr(&S.excl[par][1][(my_v % KL_TILE) >> 5], 1u << (my_v & 31));
       }
-      // rows of this warp: lanes 0 .. cnt-1
-      const int cnt = items > warp ? (items - 1 - warp) / KLF_ROW_WARPS + 1 : 0;
       int inc = my_len;
 #pragma unroll
       for (int d = 1; d < 32; d <<= 1) {
         const int t = __shfl_up_sync(FULL_MASK, inc, d);
         if (lane >= d) inc += t;
       }
-      const int total = __shfl_sync(FULL_MASK, inc, 31);
-      const int my_off = inc - my_len;
+      if (CLOCKS && inc >= 0) KLF_FINE(12);
+      S.it_lo[tid] = my_lo;
+      S.it_len[tid] = my_len;
+      S.it_inc[tid] = inc;
+      if (lane == 31) S.wtot[warp] = inc;
       KLF_FINE(2);
-      float *stg = S.stage[warp];
-      unsigned my_st = ST_LOCK;
-      float nv = 0.0f;
-      if (cnt > 0 && total <= KLF_WCAP) {
-        if (GBITS) { if (lane < cnt) my_st = (unsigned)__ldcg(p.state + my_v) & 3u; }
-        else if (lane < cnt) my_st = bits_get(bits, my_v);
-        // every 32-entry chunk of every row of the warp is a load slot; eight slots in flight per round (a warp
-        // owns 2-3 rows of ~20 entries on the circuits: one round, one L2 round trip)
-        constexpr int SLOTS = 8;
-        int j = 0, kk = 0;                                             // current row / offset inside it (warp-uniform)
-        while (j < cnt) {
-          int32_t s_lo[SLOTS], s_n[SLOTS], s_of[SLOTS];
+      klf_bar_items();                                   // items, offsets and the exclusion bitmap are in
+      KLF_FINE(3);
+      // inclusive prefix of the warps' totals: lane j holds the entries of warps 0..j
+      int winc = lane < KLF_ROW_WARPS ? S.wtot[lane] : 0;
 #pragma unroll
-          for (int s = 0; s < SLOTS; ++s) {
-            s_n[s] = 0; s_lo[s] = 0; s_of[s] = 0;
-            if (j < cnt) {
-              const int len = __shfl_sync(FULL_MASK, my_len, j);
-              s_lo[s] = __shfl_sync(FULL_MASK, my_lo, j) + kk;
-              s_of[s] = __shfl_sync(FULL_MASK, my_off, j) + kk;
-              s_n[s] = min(32, len - kk);
-              kk += 32;
-              if (kk >= len) { ++j; kk = 0; }
-            }
-          }
-          int32_t c[SLOTS];
-          float ww[SLOTS];
-#pragma unroll
-          for (int s = 0; s < SLOTS; ++s) {
-            c[s] = -1; ww[s] = 0.0f;
-            if (lane < s_n[s]) { c[s] = __ldg(p.col + s_lo[s] + lane); ww[s] = __ldg(p.w + s_lo[s] + lane); }
-          }
-          unsigned sd[SLOTS];
-#pragma unroll
-          for (int s = 0; s < SLOTS; ++s) {
-            sd[s] = 0u;
-            if (c[s] >= 0) {
-              if (c[s] == a) sd[s] = 1u;                                 // the pair being swapped: sides after the swap
-              else if (c[s] == b) sd[s] = 0u;
-              else sd[s] = GBITS ? ((unsigned)__ldcg(p.state + c[s]) & ST_SIDE) : (bits_get(bits, c[s]) & ST_SIDE);
-            }
-          }
-#pragma unroll
-          for (int s = 0; s < SLOTS; ++s)
-            if (c[s] >= 0) stg[s_of[s] + lane] = sd[s] ? ww[s] : -ww[s];
+      for (int d = 1; d < 16; d <<= 1) {
+        const int t = __shfl_up_sync(FULL_MASK, winc, d);
+        if (lane >= d) winc += t;
+      }
+      const int total = __shfl_sync(FULL_MASK, winc, KLF_ROW_WARPS - 1);
+      const int my_base = __shfl_sync(FULL_MASK, winc, warp) - __shfl_sync(FULL_MASK, inc, 31);   // first flat entry of this warp's items
+      float *stg = S.stage;
+      if (total <= KLF_ENT) {
+        // ---- ENTRIES: thread t owns the K consecutive flat entries from t*K: ONE search names the row of the first (4
+        //      shuffle steps over the warps' totals, 5 shared-memory steps over that warp's offsets), the rest follow by
+        //      walking; the loads of a chunk of 4 are in flight together; the signed weights go to stage[] ----
+        const int K = (total + KLF_ROW_THREADS - 1) / KLF_ROW_THREADS;         // 1 .. KLF_ENT / KLF_ROW_THREADS + 1
+        const int32_t g = tid * K;
+        int w = 0, wb = 0;                                                      // the item warp that holds entry g, the entries below it
+        const int n_item_warps = (items + 31) >> 5;                             // 2 on ibm10, 1 on the synthetic circuits
+#pragma unroll 1
+        for (int cand = 1; cand < n_item_warps; ++cand) {
+          const int below = __shfl_sync(FULL_MASK, winc, cand - 1);             // entries of warps 0..cand-1
+          if (below <= g) { w = cand; wb = below; }
         }
-        __syncwarp();
-        KLF_FINE(3);
-        if (lane < cnt) {
-          // the two ordered sums of cKL.cpp:225-251: E over the external weights, I over the internal ones, row order
-          float E = 0.0f, I = 0.0f;
-          const float *src = stg + my_off;
-          for (int t = 0; t < my_len; ++t) {
-            const float x = src[t];
-            E = __fadd_rn(E, fmaxf(x, 0.0f));
-            I = __fadd_rn(I, fmaxf(-x, 0.0f));
+        if (g < total) {
+          const int32_t local = g - wb;
+          const int32_t *incs = S.it_inc + w * 32;
+          int k = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int cand = k + step;
+            if (incs[cand - 1] <= local) k = cand;
           }
-          nv = __fsub_rn(E, I);
-          klf_publish<ASC>(X, my_v, my_id, my_st, nv);
+          int32_t item = w * 32 + k;
+          int32_t pos = local - (k > 0 ? incs[k - 1] : 0);
+          int32_t row_lo = S.it_lo[item], row_len = S.it_len[item];
+          if (CLOCKS && row_len >= 0) KLF_FINE(13);
+          const int32_t mine = min(K, total - g);
+          for (int j0 = 0; j0 < mine; j0 += 4) {
+            int32_t e4[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              e4[jj] = -1;
+              if (j0 + jj < mine) {
+                e4[jj] = row_lo + pos;
+                if (++pos == row_len) { ++item; row_lo = S.it_lo[item]; row_len = S.it_len[item]; pos = 0; }
+              }
+            }
+            int32_t c4[4];
+            float w4[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              c4[jj] = -1; w4[jj] = 0.0f;
+              if (e4[jj] >= 0) { c4[jj] = __ldg(p.col + e4[jj]); w4[jj] = __ldg(p.w + e4[jj]); }
+            }
+            unsigned s4[4];
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj) {
+              s4[jj] = 0u;
+              if (c4[jj] >= 0) {
+                if (c4[jj] == a) s4[jj] = 1u;                          // the pair being swapped: sides after the swap
+                else if (c4[jj] == b) s4[jj] = 0u;
+                else s4[jj] = GBITS ? ((unsigned)__ldcg(p.state + c4[jj]) & ST_SIDE) : (bits_get(bits, c4[jj]) & ST_SIDE);
+              }
+            }
+#pragma unroll
+            for (int jj = 0; jj < 4; ++jj)
+              if (c4[jj] >= 0) stg[g + j0 + jj] = s4[jj] ? w4[jj] : -w4[jj];
+          }
         }
         KLF_FINE(4);
-      } else if (cnt > 0) {
-        // the warp's rows do not fit its slice (a hub row): warp-per-row replay, one row after the other
-        for (int j = 0; j < cnt; ++j) {
-          const int32_t v = __shfl_sync(FULL_MASK, my_v, j);
-          const uint32_t vid = __shfl_sync(FULL_MASK, my_id, j);
-          const int32_t lo = __shfl_sync(FULL_MASK, my_lo, j), hi = lo + __shfl_sync(FULL_MASK, my_len, j);
-          klf_row_replay<ASC, GBITS>(p, X, bits, v, vid, lo, hi, stg);
+        klf_bar_rows();                                  // every signed weight of this swap is staged
+        KLF_FINE(5);
+        // ---- SUMS: the two ordered sums of cKL.cpp:225-251 -- E over the external weights, I over the internal ones, row
+        //      order -- then the key.  A 64-bit shared-memory atomicMax is a compare-and-swap loop (~350 cycles measured,
+        //      tools/micro/prims.cu); the keys are raised in two passes of native 32-bit atomics instead: the D words
+        //      first (a raiser clears the id word), then, behind a barrier, the id words of whoever holds the final D ----
+        bool pub = false;
+        uint32_t khi = 0u, klo = 0u;
+        unsigned long long *kp = nullptr, *gp = nullptr;
+        if (tid < items) {
+          if (!GBITS) my_st = bits_get(bits, my_v);
+          float E = 0.0f, I = 0.0f;
+          const float *src = stg + my_base + (inc - my_len);
+          // batches of 8, the next batch's loads in flight while this one is added; a batch is padded with +0.0f, which
+          // changes neither sum (E, I >= +0)
+          float cur[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) cur[q] = q < my_len ? src[q] : 0.0f;
+          for (int t = 0; t < my_len; t += 8) {
+            float nxt[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) nxt[q] = (t + 8 + q) < my_len ? src[t + 8 + q] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              E = __fadd_rn(E, fmaxf(cur[q], 0.0f));
+              I = __fadd_rn(I, fmaxf(-cur[q], 0.0f));
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) cur[q] = nxt[q];
+          }
+          const float nv = __fsub_rn(E, I);
+          if (CLOCKS && nv != 1e30f) KLF_FINE(15);
+          __stcg(p.val + my_v, nv);
+          if (!((my_st & ST_LOCK) || my_v == a || my_v == b)) {
+            const unsigned sd = my_st & ST_SIDE;
+            khi = float_orderable(sd ? -nv : nv);
+            klo = 0xFFFFFFFFu - my_id;
+            const int32_t tile = my_v / KL_TILE;
+            if (tile == ta || tile == tb) {               // the early warp of that tile folds this in after the barrier
+              kp = &S.pkey[par][tile == ta ? 0 : 1][sd];
+              atomicMax(key_hi(kp), khi);
+              pub = true;
+            } else {
+              kp = keys + 2 * tile + sd;
+              const unsigned long long cur = *reinterpret_cast<volatile unsigned long long *>(kp);
+              const unsigned long long nk = ((unsigned long long)khi << 32) | klo;
+              if (cur != 0ull && (uint32_t)(cur & 0xFFFFFFFFull) == klo && nk < cur) {
+                // v held the tile's best key and lost ground: the tile is rescanned
+                if (atomicExch(stamps + tile, stamp) != stamp) {
+                  const int slot = atomicAdd(&S.nlist[par], 1);
+                  if (slot < KLF_LCAP) S.list[par][slot] = tile;
+                }
+              } else {
+                pub = true;
+                gp = gkeys + 2 * (tile / KL_GROUP) + sd;
+                if (atomicMax(key_hi(kp), khi) < khi) {
+                  *reinterpret_cast<volatile uint32_t *>(key_lo(kp)) = 0u;
+                  if (atomicMax(key_hi(gp), khi) < khi) *reinterpret_cast<volatile uint32_t *>(key_lo(gp)) = 0u;
+                }
+              }
+            }
+          }
+        }
+        klf_bar_rows();                                  // every D word is final
+        if (pub) {
+          if (*reinterpret_cast<volatile uint32_t *>(key_hi(kp)) == khi) atomicMax(key_lo(kp), klo);
+          if (gp != nullptr && *reinterpret_cast<volatile uint32_t *>(key_hi(gp)) == khi) atomicMax(key_lo(gp), klo);
+        }
+        KLF_FINE(6);
+      } else {
+        // more entries than the staging buffer holds (a hub among the neighbours): warp-per-row replay over the item list
+        KlfCtx X;
+        make_ctx(X);
+        float *wsm = S.stage + warp * 64;
+        for (int32_t it = warp; it < items; it += KLF_ROW_WARPS) {
+          const int32_t e = it < da ? alo + it : blo + (it - da);
+          const int32_t v = __ldg(p.col + e);
+          const int2 ext = __ldg(p.nb + e);
+          const uint32_t vid = ASC ? (uint32_t)v : __ldg(p.rank + v);
+          klf_row_replay<ASC, GBITS>(p, X, bits, v, vid, ext.x, ext.y, wsm);
         }
       }
     } else {
-      // ---- more neighbours than threads (industry2-class hubs): warp-per-row over the whole list ----
-      float *stg = S.stage[warp];
+      // ---- more neighbours than row threads (industry2-class hubs): exclusion marks, then warp-per-row over the list ----
+      for (int32_t it = tid; it < items; it += KLF_ROW_THREADS) {
+        const int32_t e = it < da ? alo + it : blo + (it - da);
+        const int32_t v = __ldg(p.col + e);
+        const int32_t tv = v / KL_TILE;
+        if (tv == ta) atomicOr(&S.excl[par][0][(v % KL_TILE) >> 5], 1u << (v & 31));
+        else if (tv == tb) atomicOr(&S.excl[par][1][(v % KL_TILE) >> 5], 1u << (v & 31));
+      }
+      klf_bar_items();
+      KlfCtx X;
+      make_ctx(X);
+      float *wsm = S.stage + warp * 64;
       for (int32_t it = warp; it < items; it += KLF_ROW_WARPS) {
         const int32_t e = it < da ? alo + it : blo + (it - da);
         const int32_t v = __ldg(p.col + e);
         const int2 ext = __ldg(p.nb + e);
         const uint32_t vid = ASC ? (uint32_t)v : __ldg(p.rank + v);
-        klf_row_replay<ASC, GBITS>(p, X, bits, v, vid, ext.x, ext.y, stg);
+        klf_row_replay<ASC, GBITS>(p, X, bits, v, vid, ext.x, ext.y, wsm);
       }
     }
-    KLF_FINE(5);
-    __syncthreads();                                   // (A) every D-value, patch, raise and rescan request of this swap is in
-    KLF_FINE(6);
-    // ---- S4: rescans.  Early tiles from the values loaded at the top, patched; late tiles with one round trip ----
+    KLF_FINE(7);
+    __syncthreads();                                   // (A) every D-value, published key and rescan request of this swap is in
+    KLF_FINE(8);
+    // ---- S4: the early tiles' keys = max(base, published); group keys; late rescans (rare) ----
     const int nl = S.nlist[par];
-    if (early) {
-      unsigned long long e0 = 0ull, e1 = 0ull;
-      const int s = (warp == KLF_ROW_WARPS - 2) ? 0 : 1;
-#pragma unroll
-      for (int r = 0; r < KL_TILE / 32; ++r) {
-        const int idx = r * 32 + lane;
-        const int32_t u = et * KL_TILE + idx;
-        if (u >= p.n || u == a || u == b) continue;
-        const unsigned st = GBITS ? esg[r] : bits_get(bits, u);
-        if (st & ST_LOCK) continue;
-        const float x = (S.pstamp[s][idx] == stamp) ? S.patch[s][idx] : ev[r];
-        const unsigned long long key = kl_key<ASC>(x, st & ST_SIDE, eid[r]);
-        if (st & ST_SIDE) e1 = key > e1 ? key : e1; else e0 = key > e0 ? key : e0;
+    const int32_t gA = ta / KL_GROUP, gB = tb / KL_GROUP;
+    if (early && lane == 0) {
+      const unsigned long long q0 = S.pkey[par][es][0], q1 = S.pkey[par][es][1];
+      keys[2 * et] = base0 > q0 ? base0 : q0;
+      keys[2 * et + 1] = base1 > q1 ? base1 : q1;
+    }
+    if (nl == 0) {
+      // common case: only the groups of the two early tiles changed downwards; their warps refold them
+      if (warp == KLF_E1 && early) {
+        __syncwarp();
+        if (gB != gA) group_fold(gB);
+        klf_bar_early_arrive();
+      } else if (warp == KLF_E0) {
+        __syncwarp();
+        if (tb != ta && gB == gA) klf_bar_early_sync();
+        group_fold(gA);
+        if (tb != ta && gB != gA) klf_bar_early_sync();
+        __syncwarp();
+        // the next swap's pair selection, while the other warps are on their way to the barrier
+        unsigned long long k0 = 0ull, k1 = 0ull;
+#pragma unroll 1
+        for (int32_t g = lane; g < n_groups; g += 32) {
+          const unsigned long long a0 = gkeys[2 * g], a1 = gkeys[2 * g + 1];
+          k0 = a0 > k0 ? a0 : k0;
+          k1 = a1 > k1 ? a1 : k1;
+        }
+        k0 = warp_max_u64(k0); k1 = warp_max_u64(k1);
+        if (lane == 0) { S.best[0] = k0; S.best[1] = k1; S.best_stamp = stamp; }
       }
-      e0 = warp_max_u64(e0);
-      e1 = warp_max_u64(e1);
-      if (lane == 0) {
-        keys[2 * et] = e0; keys[2 * et + 1] = e1;
-        const int32_t g = et / KL_GROUP;
-        if (atomicExch(gstamp + g, stamp) != stamp) S.dlist[par][atomicAdd(&S.ndirty[par], 1)] = g;
-      }
-    } else if (warp < KLF_ROW_WARPS - 2) {
-      for (int q = warp; q < nl; q += KLF_ROW_WARPS - 2) {
-        const int32_t t = S.list[par][q];
-        klf_tile_rescan<ASC, GBITS>(p, bits, t, keys);
+    } else if (nl > KLF_LCAP) {
+      // more rescan requests than the list holds (only a hub swap can do that): rebuild every key
+      for (int32_t t = warp; t < p.n_tiles; t += KLF_WARPS) klf_tile_rescan<ASC, GBITS>(p, bits, t, keys);
+      __syncthreads();
+      for (int32_t g = warp; g < n_groups; g += KLF_WARPS) group_fold(g);
+    } else {
+      if (early) {
         if (lane == 0) {
-          const int32_t g = t / KL_GROUP;
+          const int32_t g = et / KL_GROUP;
           if (atomicExch(gstamp + g, stamp) != stamp) S.dlist[par][atomicAdd(&S.ndirty[par], 1)] = g;
         }
+      } else if (warp < KLF_ROW_WARPS) {
+        for (int q = warp; q < nl; q += KLF_ROW_WARPS) {
+          const int32_t t = S.list[par][q];
+          klf_tile_rescan<ASC, GBITS>(p, bits, t, keys);
+          if (lane == 0) {
+            const int32_t g = t / KL_GROUP;
+            if (atomicExch(gstamp + g, stamp) != stamp) S.dlist[par][atomicAdd(&S.ndirty[par], 1)] = g;
+          }
+        }
       }
-    }
-    if (p.clocks && tid == 0) S.fine[14] += nl;
-    KLF_FINE(7);
-    __syncthreads();                                   // (B) tile keys final
-    KLF_FINE(8);
-    {
+      __syncthreads();                                 // (B) tile keys final
       const int nd = S.ndirty[par];
       for (int q = warp; q < nd; q += KLF_WARPS) group_fold(S.dlist[par][q]);
     }
-    __syncthreads();                                   // (C) group keys final
+    if (CLOCKS && tid == 0) S.fine[14] += nl;
     KLF_FINE(9);
+    __syncthreads();                                   // (C) group keys final
+    KLF_FINE(10);
   }
   __syncthreads();
   if (tid == 0) {
     p.ctrl[0] = (int64_t)S.iter; p.ctrl[1] = 1;
-    if (p.clocks)
+    if (CLOCKS)
       for (int i = 0; i < 16; ++i) p.ctrl[16 + i] = S.fine[i];
   }
 #undef KLF_FINE
@@ -1480,6 +1652,15 @@ __global__ void kl_undo_kernel(const int32_t *__restrict__ n1, const int32_t *__
   if (i > to) return;
   state[n1[i]] = (uint8_t)ST_LOCK;                   // back on side 0 (still marked: the pass is over)
   state[n2[i]] = (uint8_t)(ST_SIDE | ST_LOCK);       // back on side 1
+}
+// reads the swap loop's arrays once so that its dependent loads find them in L2 (tuning experiment, EIGKL_KL_WARM)
+__global__ void kl_warm_kernel(const uint4 *__restrict__ p, size_t n16, unsigned *__restrict__ sink) {
+  unsigned s = 0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 v = __ldcg(p + i);
+    s += v.x ^ v.y ^ v.z ^ v.w;
+  }
+  if (s == 0x9E3779B9u) *sink = s;
 }
 int64_t kl_rollback(eigkl_handle *h, float *best_cut) {
   auto &k = h->kl;
@@ -1541,6 +1722,7 @@ void kl_run(eigkl_handle *h) {
   EIGKL_CUDA(cudaMemcpyAsync(k.t_n1.p, &neg, sizeof(int32_t), cudaMemcpyHostToDevice, st));
   EIGKL_CUDA(cudaMemcpyAsync(k.t_n2.p, &neg, sizeof(int32_t), cudaMemcpyHostToDevice, st));
   EIGKL_CUDA(cudaMemsetAsync(k.ctrl.p, 0, 4 * sizeof(int64_t), st));
+  EIGKL_CUDA(cudaMemsetAsync(k.ctrl.p + 40, 0, 8 * sizeof(int64_t), st));
   h->timer.stop(st);
   h->stats.ms_kl_setup = h->timer.ms();
 
@@ -1577,6 +1759,13 @@ void kl_run(eigkl_handle *h) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
+  if (local && getenv("EIGKL_KL_WARM")) {
+    auto warm = [&](const void *ptr, size_t bytes) {
+      kl_warm_kernel<<<592, 256, 0, st>>>(reinterpret_cast<const uint4 *>(ptr), bytes / 16, reinterpret_cast<unsigned *>(k.ctrl.p + 3));
+    };
+    warm(A.nb.p, (size_t)2 * A.nnz * 4); warm(A.col.p, (size_t)A.nnz * 4); warm(A.w.p, (size_t)A.nnz * 4);
+    warm(A.rowptr.p, (size_t)n * 4); warm(k.val.p, (size_t)n * 4);
+  }
   h->timer.start(st);
   if (local) {
     KlLocalParams q;
@@ -1600,22 +1789,24 @@ void kl_run(eigkl_handle *h) {
     if (flat) {
       const size_t n_groups = (size_t)ceil_div(n_tiles, KL_GROUP);
       const size_t fsmem = (size_t)n_tiles * 20 + n_groups * 20 + sizeof(KlFlatSmem) + (gbits ? 0 : (size_t)((n + 15) / 16) * 4) + 16;
-      if (!h->attr_kl_flat) {
-        const size_t lim = 227 * 1024;
-        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-        EIGKL_CUDA(cudaFuncSetAttribute(kl_loop_flat_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lim));
-        h->attr_kl_flat = true;
-      }
+      const int variant = (k.ascending ? 4 : 0) | (gbits ? 2 : 0) | (q.clocks ? 1 : 0);
+      auto launch_flat = [&](auto kern) {
+        if (!(h->attr_kl_flat & (1u << variant))) {
+          EIGKL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          h->attr_kl_flat |= 1u << variant;
+        }
+        kern<<<1, KLF_THREADS, fsmem, st>>>(q);       // (147 sleeping "company" CTAs were tried against the lone-CTA issue throttle: no effect)
+      };
       EIGKL_REQUIRE(fsmem <= 227 * 1024, EIGKL_E_ARG, "KL flat loop: shared-memory plan exceeds the SM");
-      const unsigned fgrid = 1;       // (147 sleeping "company" CTAs were tried against the lone-CTA issue throttle: no effect)
-      if (k.ascending) {
-        if (gbits) kl_loop_flat_kernel<true, true><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
-        else kl_loop_flat_kernel<true, false><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
-      } else {
-        if (gbits) kl_loop_flat_kernel<false, true><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
-        else kl_loop_flat_kernel<false, false><<<fgrid, KLF_THREADS, fsmem, st>>>(q);
+      switch (variant) {
+        case 0: launch_flat(kl_loop_flat_kernel<false, false, false>); break;
+        case 1: launch_flat(kl_loop_flat_kernel<false, false, true>); break;
+        case 2: launch_flat(kl_loop_flat_kernel<false, true, false>); break;
+        case 3: launch_flat(kl_loop_flat_kernel<false, true, true>); break;
+        case 4: launch_flat(kl_loop_flat_kernel<true, false, false>); break;
+        case 5: launch_flat(kl_loop_flat_kernel<true, false, true>); break;
+        case 6: launch_flat(kl_loop_flat_kernel<true, true, false>); break;
+        default: launch_flat(kl_loop_flat_kernel<true, true, true>); break;
       }
     } else if (k.ascending) {
       if (gbits) kl_loop_local_kernel<true, true><<<1, KL_LOOP_THREADS, smem, st>>>(q);
@@ -1655,7 +1846,7 @@ void kl_run(eigkl_handle *h) {
     }
   }
   h->timer.stop(st);
-  int64_t ctrl[32] = {0};
+  int64_t ctrl[48] = {0};
   EIGKL_CUDA(cudaMemcpyAsync(ctrl, k.ctrl.p, sizeof(ctrl), cudaMemcpyDeviceToHost, st));
   EIGKL_CUDA(cudaStreamSynchronize(st));
   EIGKL_CUDA(cudaGetLastError());
@@ -1670,10 +1861,12 @@ void kl_run(eigkl_handle *h) {
     for (int i = 0; i < 6; ++i) fprintf(stderr, " %s %.0f;", nm[i], (double)ctrl[8 + i] / (double)k.swaps);
     fprintf(stderr, "\n");
     if (local && flat) {
-      static const char *fn[10] = {"S1 group fold", "decode+rowptr (+early loads issued)", "nbr entries arrive + scan", "rows staged", "row sums + publish",
-                                   "S3 tail", "barrier A", "rescans", "barrier B", "group refold + barrier C"};
+      static const char *fn[11] = {"S1 (pair selection)", "decode+rowptr (+early loads issued)", "item loads + scan", "items barrier", "entry search + loads + stage",
+                                   "entries barrier", "row sums + two-pass publish", "S3 tail", "barrier A", "early keys + group refold (+ late rescans)", "barrier C"};
       fprintf(stderr, "[eigkl] KL flat-loop probes, cycles per swap (thread 0):");
-      for (int i = 0; i < 10; ++i) fprintf(stderr, " %s %.0f;", fn[i], (double)ctrl[16 + i] / (double)k.swaps);
+      for (int i = 0; i < 11; ++i) fprintf(stderr, " %s %.0f;", fn[i], (double)ctrl[16 + i] / (double)k.swaps);
+      fprintf(stderr, " [sub-probes: item loads arrived %.0f; scan done %.0f; entry search done %.0f; sums done %.0f]", (double)ctrl[16 + 11] / (double)k.swaps,
+              (double)ctrl[16 + 12] / (double)k.swaps, (double)ctrl[16 + 13] / (double)k.swaps, (double)ctrl[16 + 15] / (double)k.swaps);
       fprintf(stderr, " late rescans per swap %.2f\n", (double)ctrl[16 + 14] / (double)k.swaps);
     } else if (local) {
       static const char *fn[13] = {"S1 local max", "S1 barrier 1", "S1 final max", "S1 barrier 2", "decode+rowptr", "nbr entries arrive",

@@ -282,9 +282,11 @@ struct DistArgs {
   uint32_t wait_seq, push_seq;
   unsigned int *ticket;
   int *err;
+  int diag;                            // EIGKL_DIST_DIAG (timing experiments, results invalid): 1 no export stores, 2 no per-CTA system fence, 4 no flag wait
 };
 
 __device__ __forceinline__ void dist_wait_flags(const DistArgs &D) {
+  if (D.diag & 4) return;
   if (threadIdx.x < (unsigned)D.R && (int)threadIdx.x != D.me) {
     const unsigned int *f = D.flags + threadIdx.x;
     unsigned int v;
@@ -376,12 +378,13 @@ spmv_dist_kernel(const int32_t *__restrict__ rowptr, const double *__restrict__ 
     const int32_t s = D.blk_exp[(size_t)blockIdx.x * D.R + q], e = D.blk_exp[(size_t)(blockIdx.x + 1) * D.R + q];
     double *dst = reinterpret_cast<double *>(D.peers[q] + D.out_off) + (size_t)D.me * D.n_pad;
     const int32_t *ids = D.exp_ids + (size_t)q * D.n_pad;
+    if (D.diag & 1) continue;
     for (int32_t i = s + lane; i < e; i += 32) {
       const int32_t rl = ids[i];                                   // local row offset
       dst[i] = flat ? ys[rl - (r0 - row_offset)] : __ldcg(y + rl);
     }
   }
-  __threadfence_system();
+  if (D.diag & 2) __threadfence(); else __threadfence_system();
   __syncthreads();
   if (tid == 0) am_last = (atomicInc(D.ticket, gridDim.x - 1) == gridDim.x - 1);
   __syncthreads();
@@ -850,6 +853,8 @@ void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const d
     D.n_pad = P.n_pad; D.me = P.me; D.R = P.R;
     D.wait_seq = dist->wait_seq; D.push_seq = dist->push_seq;
     D.ticket = h->arena.ticket.p + 1; D.err = h->arena.err.p;
+    static const int diag = getenv("EIGKL_DIST_DIAG") ? atoi(getenv("EIGKL_DIST_DIAG")) : 0;
+    D.diag = diag;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3((unsigned)L.n_blocks);
     cfg.blockDim = dim3(SPMV_THREADS);
