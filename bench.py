@@ -401,7 +401,9 @@ def measure(cx, name, steps, warmup, primary):
                           "us_per_swap": 1e3 * s1["ms_kl_loop"] / max(1, s1["kl_swaps"]),
                           "state": {0: "global memory (cluster kernel)", 1: "tile keys + side bits in shared memory",
                                     2: "tile keys in shared memory, state bytes in global memory"}.get(int(s1.get("kl_local", 0)), "?"),
-                          "bound": "latency (a chain of dependent L2 round trips per swap), not bandwidth"}
+                          "form": "flat (by entry), 512 threads" if int(s1.get("kl_flat", 0)) else "warp per row / cluster",
+                          "bound": "latency and instruction supply of ONE CTA (four dependent L2/DRAM trips + ~600 dependent on-chip steps per swap), "
+                                   "not bandwidth: reported as us per swap"}
     if kernels.get("multidot") and s1.get("gs_fused", 0):
         kernels["multidot"]["note"] = ("fused Gram-Schmidt: ONE cooperative launch per Lanczos step does both passes "
                                        "(h1, update, h2, update, DGKS decision, norm); %d basis columns cached in shared memory; "
@@ -411,11 +413,13 @@ def measure(cx, name, steps, warmup, primary):
         kernels["exchange"] = {
             "halo_values_received_per_spmv": int(s1["dist_halo"]), "rows_pushed_per_spmv": int(s1["dist_exports"]),
             "rows_of_this_rank": int(s1["dist_rows"]),
-            "nccl_allreduce": {"calls": int(ncm), "us_avg": 1e3 * (s1["ms_comm"] - s0["ms_comm"]) / max(1, ncm),
-                               "ms_total": s1["ms_comm"] - s0["ms_comm"]},
+            "allreduce": {"calls": int(ncm), "us_avg": 1e3 * (s1["ms_comm"] - s0["ms_comm"]) / max(1, ncm),
+                          "ms_total": s1["ms_comm"] - s0["ms_comm"],
+                          "how": "one-shot all-reduce over the peer-mapped arena (dist_allreduce_kernel: tagged 16-byte words stored "
+                                 "into every peer, summed in rank order); the time includes waiting for the slowest rank"},
             "standalone_halo_push": {"launches": int(nps), "us_avg": 1e3 * (s1["ms_push"] - s0["ms_push"]) / max(1, nps)},
             "note": "rank 0's view; every SpMV but the first of a filter application pushes its export rows from its own epilogue "
-                    "(inside the spmv class above); the Lanczos dot products / norms are ncclAllReduce calls"}
+                    "(inside the spmv class above, which also holds the one-warp flag kernel behind every pushing SpMV); no NCCL call on the data path"}
     if spmv_iso is not None:
         kernels["spmv_isolated"] = {"us_avg_l2_warm": spmv_iso * 1e3, "us_avg_l2_flushed": spmv_cold * 1e3,
                                     "gbs_l2_warm": s1["bytes_spmv"] / (spmv_iso * 1e-3) / 1e9,
@@ -499,7 +503,8 @@ def measure(cx, name, steps, warmup, primary):
     torch.cuda.empty_cache()
     if st["dist_ranks"] > 1:
         par = ("Lanczos row-partitioned over %d ranks: nnz-balanced row cuts, packed halos pushed over NVLink from the SpMV epilogue "
-               "(peer-mapped memory, flags), NCCL all-reduces for the dot products; assembly and the latency-bound KL pass replicated" % world)
+               "(peer-mapped memory, flags), one-shot all-reduces of the Lanczos dot products over the same peer memory; assembly and the "
+               "latency-bound KL pass replicated" % world)
     elif world > 1:
         par = "the matrix fits one chip: every one of the %d ranks solves the whole problem (replicas of ONE bipartition), no data-path collective" % world
     else:

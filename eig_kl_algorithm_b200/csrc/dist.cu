@@ -40,7 +40,11 @@ __device__ __forceinline__ int rank_of(const Cuts &k, int32_t row) {
 }
 }  // namespace
 
-// cut r = the row (a multiple of 32) closest to holding r/R of the non-zeros
+// cut r = the row (a multiple of 32) closest to holding r/R of the solve's bytes: 12 per non-zero (value + column) and
+// DIST_ROW_BYTES per row -- the SpMV's 28 (row pointer, x, z, y) plus the row's share of the Gram-Schmidt passes, which
+// stream the basis: 4 passes x ~50 columns x 8 bytes per Lanczos step = ~100 bytes per row and SpMV at filter degree 16.
+// Balancing the non-zeros alone gave one of two ranks 50 % more rows at 2 M nodes (multidot 69 vs 52 us).
+constexpr long long DIST_ROW_BYTES = 128;
 __global__ void dist_cuts_kernel(const int32_t *__restrict__ rowptr, int32_t n, int R, int32_t *__restrict__ cuts /* R+1, then R+1 entry offsets */) {
   const int r = threadIdx.x;
   if (r > R) return;
@@ -48,12 +52,12 @@ __global__ void dist_cuts_kernel(const int32_t *__restrict__ rowptr, int32_t n, 
   if (r == 0) row = 0;
   else if (r == R) row = n;
   else {
-    const int64_t nnz = rowptr[n];
-    const int64_t target = nnz * r / R;
+    const int64_t total = 12ll * rowptr[n] + DIST_ROW_BYTES * n;
+    const int64_t target = total * r / R;
     int32_t lo = 0, hi = n;
     while (lo < hi) {
       const int32_t mid = (lo + hi) >> 1;
-      if ((int64_t)rowptr[mid] < target) lo = mid + 1; else hi = mid;
+      if (12ll * rowptr[mid] + DIST_ROW_BYTES * mid < target) lo = mid + 1; else hi = mid;
     }
     row = (int32_t)min((int64_t)n, ((int64_t)lo + 16) / 32 * 32);
   }
@@ -210,6 +214,7 @@ static bool peer_arena_ensure(eigkl_handle *h, size_t vec_bytes) {
   a.bytes = bytes;
   a.state = 1;
   a.seq = 0;
+  a.red_seq = 0;
   a.dev_ptrs.alloc(EIGKL_MAX_RANKS);
   unsigned long long tbl[EIGKL_MAX_RANKS] = {0};
   for (int q = 0; q < R; ++q) tbl[q] = (unsigned long long)(uintptr_t)a.peer[q];
@@ -318,27 +323,13 @@ void dist_plan(eigkl_handle *h) {
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 halo_push_kernel(const double *__restrict__ own, const int32_t *__restrict__ exp_ids, const int32_t *__restrict__ exp_cnt,
-                 const unsigned long long *__restrict__ peers, size_t buf_off, int32_t n_pad, int me, int R, uint32_t seq,
-                 unsigned int *__restrict__ ticket) {
-  __shared__ bool am_last;
+                 const unsigned long long *__restrict__ peers, size_t buf_off, int32_t n_pad, int me) {
   const int q = blockIdx.y;
-  if (q != me) {
-    const int32_t cnt = exp_cnt[q];
-    double *dst = reinterpret_cast<double *>(peers[q] + buf_off) + (size_t)me * n_pad;
-    const int32_t *ids = exp_ids + (size_t)q * n_pad;
-    for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) dst[i] = own[ids[i]];
-  }
-  __threadfence_system();
-  __syncthreads();
-  const unsigned total = gridDim.x * gridDim.y;
-  if (threadIdx.x == 0) am_last = (atomicInc(ticket, total - 1) == total - 1);
-  __syncthreads();
-  if (!am_last) return;
-  __threadfence_system();
-  if (threadIdx.x < (unsigned)R && (int)threadIdx.x != me) {
-    unsigned int *flag = reinterpret_cast<unsigned int *>(peers[threadIdx.x]) + me;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
-  }
+  if (q == me) return;
+  const int32_t cnt = exp_cnt[q];
+  double *dst = reinterpret_cast<double *>(peers[q] + buf_off) + (size_t)me * n_pad;
+  const int32_t *ids = exp_ids + (size_t)q * n_pad;
+  for (int32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += gridDim.x * blockDim.x) dst[i] = own[ids[i]];
 }
 
 uint32_t dist_push(eigkl_handle *h, int b) {
@@ -347,13 +338,13 @@ uint32_t dist_push(eigkl_handle *h, int b) {
   const uint32_t seq = ++a.seq;
   int32_t most = 1;
   for (int q = 0; q < D.R; ++q) most = std::max(most, D.exp_cnt_host[q]);
-  dim3 grid((unsigned)std::min<int64_t>(64, ceil_div(most, 1024)), (unsigned)D.R);
+  dim3 grid((unsigned)std::min<int64_t>(256, ceil_div(most, 1024)), (unsigned)D.R);
   const size_t off = PEER_FLAGS_BYTES + (size_t)b * a.vec_bytes;
   h->prof.begin(KC_PUSH, h->stream);
-  halo_push_kernel<<<grid, 256, 0, h->stream>>>(dist_own(h, b), D.exp_ids.p, D.exp_cnt.p, a.dev_ptrs.p, off, D.n_pad, D.me, D.R, seq,
-                                                a.ticket.p);
-  h->prof.end(h->stream);
+  halo_push_kernel<<<grid, 256, 0, h->stream>>>(dist_own(h, b), D.exp_ids.p, D.exp_cnt.p, a.dev_ptrs.p, off, D.n_pad, D.me);
   h->launches++;
+  dist_raise_flags(h, seq);                        // the stores of the kernel above are complete when this one starts
+  h->prof.end(h->stream);
   return seq;
 }
 
@@ -369,8 +360,55 @@ void dist_check(eigkl_handle *h) {
   EIGKL_CUDA(cudaStreamSynchronize(h->stream));
   if (e[0] != 0) {
     EIGKL_CUDA(cudaMemsetAsync(h->arena.err.p, 0, sizeof(e), h->stream));
-    throw Error(EIGKL_E_NCCL, "row-partitioned SpMV: a peer's halo did not arrive (flag wait timed out; ranks out of step?)");
+    throw Error(EIGKL_E_NCCL, e[0] == 2 ? "row-partitioned solve: a peer's partial sums did not arrive (all-reduce wait timed out; ranks out of step?)"
+                                        : "row-partitioned SpMV: a peer's halo did not arrive (flag wait timed out; ranks out of step?)");
   }
+}
+
+
+// ---------------------------------------------------------------------------------------------------
+// One-shot all-reduce of <= 128 doubles over the peer-mapped arena (the Gram-Schmidt coefficients and the norms of a
+// Lanczos step; an ncclAllReduce of that size measured 35 us per call, 280 calls per solve at 2 M nodes).  Every rank
+// stores its partials into slot `me` of every rank's reduce area as 16-byte {lo, tag, hi, tag} words (8-byte stores are
+// single-copy atomic, over NVLink too: a reader that sees both tags has the value -- no fence, no flag), then polls the
+// R slots of its own area and adds them in rank order: the same sum, bit for bit, on every rank.  Two areas alternate:
+// a rank can be at most one reduction ahead of a peer that has not yet read the previous one.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(DIST_RED_MAX)
+dist_allreduce_kernel(double *__restrict__ buf, int count, const unsigned long long *__restrict__ peers, int me, int R, uint32_t tag, int parity,
+                      int *__restrict__ err) {
+  const int t = threadIdx.x;
+  if (t >= count) return;
+  const double mine = buf[t];
+  const unsigned long long bits = (unsigned long long)__double_as_longlong(mine);
+  const unsigned long long w0 = (bits & 0xFFFFFFFFull) | ((unsigned long long)tag << 32), w1 = (bits >> 32) | ((unsigned long long)tag << 32);
+  const size_t slot = PEER_RED_OFFSET + (((size_t)parity * EIGKL_MAX_RANKS + me) * DIST_RED_MAX + t) * 16;
+  for (int q = 0; q < R; ++q) {
+    unsigned long long *dst = reinterpret_cast<unsigned long long *>(peers[q] + slot);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(dst), "l"(w0), "l"(w1) : "memory");
+  }
+  double sum = 0.0;
+  const long long t0 = clock64();
+  for (int r = 0; r < R; ++r) {
+    const unsigned long long *src = reinterpret_cast<const unsigned long long *>(peers[me] + PEER_RED_OFFSET +
+                                                                                 (((size_t)parity * EIGKL_MAX_RANKS + r) * DIST_RED_MAX + t) * 16);
+    unsigned long long a, b;
+    for (;;) {
+      asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(src) : "memory");
+      if ((uint32_t)(a >> 32) == tag && (uint32_t)(b >> 32) == tag) break;
+      if (clock64() - t0 > 6000000000ll) { atomicExch(err, 2); break; }       // ~3 s: ranks out of step; reported by dist_check
+    }
+    sum += __longlong_as_double((long long)((a & 0xFFFFFFFFull) | (b << 32)));
+  }
+  buf[t] = sum;
+}
+
+void dist_allreduce_sum(eigkl_handle *h, double *buf, size_t count) {
+  auto &a = h->arena;
+  EIGKL_REQUIRE(count <= (size_t)DIST_RED_MAX, EIGKL_E_ARG, "dist_allreduce_sum: too many values");
+  const uint32_t tag = ++a.red_seq;
+  dist_allreduce_kernel<<<1, DIST_RED_MAX, 0, h->stream>>>(buf, (int)count, a.dev_ptrs.p, h->dist.me, h->dist.R, tag, (int)(tag & 1u), a.err.p);
+  h->launches++;
 }
 
 // slice (n_pad doubles, this rank's rows) of every rank -> the full vector in natural row order on every rank

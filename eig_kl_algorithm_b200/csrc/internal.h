@@ -225,9 +225,12 @@ struct PeerArena {
   DBuf<unsigned int> ticket;     // last-CTA tickets of the push kernels
   DBuf<int> err;                 // [0] != 0: a flag wait timed out
   uint32_t seq = 0;              // halo productions issued so far (identical on every rank)
+  uint32_t red_seq = 0;          // one-shot all-reduces issued so far (identical on every rank)
   int state = 0;                 // 0 untried, 1 usable, -1 peer mapping unavailable (every rank then solves replicated)
 };
-constexpr size_t PEER_FLAGS_BYTES = 4096;
+constexpr int DIST_RED_MAX = 128;                                      // values per one-shot all-reduce
+constexpr size_t PEER_RED_OFFSET = 4096;                               // reduce areas: 2 x EIGKL_MAX_RANKS x DIST_RED_MAX x 16 bytes behind the flags
+constexpr size_t PEER_FLAGS_BYTES = PEER_RED_OFFSET + (size_t)2 * EIGKL_MAX_RANKS * DIST_RED_MAX * 16;   // flags + reduce areas; the vectors follow
 
 struct KlCsr {                 // fp32, symmetric, rows in reference traversal order
   int32_t n = 0;
@@ -381,7 +384,9 @@ int64_t dist_decide(eigkl_handle *h);                             // assemble_la
 void dist_plan(eigkl_handle *h);                                  // halo / export plan once the SpMV row blocks exist
 double *dist_buf(eigkl_handle *h, int b);                         // arena vector b (0..2 = w, 3 = stage), R x n_pad doubles
 inline double *dist_own(eigkl_handle *h, int b);
+void dist_raise_flags(eigkl_handle *h, uint32_t seq);             // spmv.cu: one-warp kernel, release.sys store of seq into every peer's flag word
 uint32_t dist_push(eigkl_handle *h, int b);                       // push the own slot's export rows of buffer b; returns its seq
+void dist_allreduce_sum(eigkl_handle *h, double *buf, size_t count);   // in place, <= DIST_RED_MAX doubles, over the arena (no NCCL)
 void dist_stage_load(eigkl_handle *h, const double *src_local);   // stage.own = src (then dist_push(h, 3))
 void dist_check(eigkl_handle *h);                                 // throws when a flag wait timed out
 void dist_gather_full(eigkl_handle *h, const double *slice, double *full_natural);   // NCCL all-gather + un-slotting

@@ -658,7 +658,8 @@ void launch_multidot(LzCtx &c, const double *V, int ncols, const double *w, doub
   }
   if (c.R > 1) {                                                       // C2: Lanczos dot products
     c.h->prof.begin(KC_COMM, c.h->stream);
-    comm_allreduce_sum_f64(c.h, h_out, (size_t)ncols);
+    if (c.h->dist.valid && ncols <= DIST_RED_MAX) dist_allreduce_sum(c.h, h_out, (size_t)ncols);
+    else comm_allreduce_sum_f64(c.h, h_out, (size_t)ncols);
     c.h->prof.end(c.h->stream);
   }
 }
@@ -686,7 +687,8 @@ void launch_update(LzCtx &c, const double *V, int ncols, double *w, const double
   }
   if (!single) {
     c.h->prof.begin(KC_COMM, c.h->stream);
-    comm_allreduce_sum_f64(c.h, e.scal.p, 1);
+    if (c.h->dist.valid) dist_allreduce_sum(c.h, e.scal.p, 1);
+    else comm_allreduce_sum_f64(c.h, e.scal.p, 1);
     c.h->prof.end(c.h->stream);
     if (pass == 1) decide_kernel<<<1, LZ_THREADS, 0, c.h->stream>>>(e.scal.p, hcoef, ncols, c.eta2, e.flag.p, e.beta.p, e.alpha.p, j);
     else beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, e.beta.p, e.alpha.p, h_prev, hcoef, j, e.flag.p);
@@ -702,7 +704,8 @@ void launch_norm(LzCtx &c, const double *w) {
     EIGKL_CUDA(cudaMemsetAsync(e.scal.p, 0, sizeof(double), c.h->stream));
   }
   if (c.R > 1) {
-    comm_allreduce_sum_f64(c.h, e.scal.p, 1);
+    if (c.h->dist.valid) dist_allreduce_sum(c.h, e.scal.p, 1);
+    else comm_allreduce_sum_f64(c.h, e.scal.p, 1);
     beta_kernel<<<1, 32, 0, c.h->stream>>>(e.scal.p, nullptr, nullptr, nullptr, nullptr, 0, nullptr);
     c.h->launches++;
   }

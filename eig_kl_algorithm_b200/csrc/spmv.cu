@@ -267,8 +267,8 @@ spmv_flat_kernel(const int32_t *__restrict__ rowptr, const int32_t *__restrict__
 //     push of the input vector (number wait_seq) has landed -- peers write the halo slots over NVLink;
 //   * the epilogue keeps the block's y values in shared memory and one warp per peer copies the block's segment of
 //     that peer's export list straight into the peer's slot `me` of the OUTPUT buffer (packed, coalesced 8-byte
-//     stores through the peer mapping); the last CTA to finish raises this rank's flag on every peer (release at
-//     system scope).  Compute, transfer and signalling are one kernel; values that nobody needs never travel.
+//     stores through the peer mapping) while other blocks still compute; a one-warp successor kernel then raises
+//     this rank's flag on every peer (release at system scope).  Values that nobody needs never travel.
 // ---------------------------------------------------------------------------------------------------
 struct DistArgs {
   const int32_t *col_c;
@@ -280,9 +280,8 @@ struct DistArgs {
   int32_t n_pad;
   int me, R;
   uint32_t wait_seq, push_seq;
-  unsigned int *ticket;
   int *err;
-  int diag;                            // EIGKL_DIST_DIAG (timing experiments, results invalid): 1 no export stores, 2 no per-CTA system fence, 4 no flag wait
+  int diag;                            // EIGKL_DIST_DIAG (timing experiments, results invalid): 1 no export stores, 4 no flag wait
 };
 
 __device__ __forceinline__ void dist_wait_flags(const DistArgs &D) {
@@ -310,7 +309,6 @@ spmv_dist_kernel(const int32_t *__restrict__ rowptr, const double *__restrict__ 
   __shared__ int32_t rp[FLAT_CAP + 1];
   __shared__ int32_t long_rows[SPMV_MAX_LONG];
   __shared__ int n_long;
-  __shared__ bool am_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   asm volatile("griddepcontrol.launch_dependents;");
   const int4 info = __ldg(blk_info + blockIdx.x);
@@ -370,30 +368,37 @@ spmv_dist_kernel(const int32_t *__restrict__ rowptr, const double *__restrict__ 
     }
   }
   (void)long_rows; (void)n_long;
-  if (D.push_seq == 0) return;
+  if (D.push_seq == 0 || (D.diag & 1)) return;
   __syncthreads();
-  // ---- push this block's export rows: warp w serves peers w, w + 8, ... ----
-  for (int q = warp; q < D.R; q += SPMV_THREADS / 32) {
+  // ---- push this block's export rows: every thread takes entries of the block's segments of the peers' export lists
+  //      (coalesced 8-byte stores through the peer mapping).  No fence, no flag here: the stores of a kernel are complete
+  //      when it ends, and dist_flag_kernel, the next launch in the stream, raises this rank's flag on every peer ----
+  for (int q = 0; q < D.R; ++q) {
     if (q == D.me) continue;
     const int32_t s = D.blk_exp[(size_t)blockIdx.x * D.R + q], e = D.blk_exp[(size_t)(blockIdx.x + 1) * D.R + q];
     double *dst = reinterpret_cast<double *>(D.peers[q] + D.out_off) + (size_t)D.me * D.n_pad;
     const int32_t *ids = D.exp_ids + (size_t)q * D.n_pad;
-    if (D.diag & 1) continue;
-    for (int32_t i = s + lane; i < e; i += 32) {
+    for (int32_t i = s + tid; i < e; i += SPMV_THREADS) {
       const int32_t rl = ids[i];                                   // local row offset
       dst[i] = flat ? ys[rl - (r0 - row_offset)] : __ldcg(y + rl);
     }
   }
-  if (D.diag & 2) __threadfence(); else __threadfence_system();
-  __syncthreads();
-  if (tid == 0) am_last = (atomicInc(D.ticket, gridDim.x - 1) == gridDim.x - 1);
-  __syncthreads();
-  if (!am_last) return;
-  __threadfence_system();
-  if (tid < D.R && tid != D.me) {
-    unsigned int *flag = reinterpret_cast<unsigned int *>(D.peers[tid]) + D.me;
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(D.push_seq) : "memory");
+}
+
+// raises this rank's flag on every peer: "my export rows of production `seq` have landed".  Launched as an ordinary
+// stream successor of the kernel that stored them (spmv_dist_kernel / halo_push_kernel), i.e. after all of its stores --
+// peer stores included -- are complete; the release at system scope orders the flag behind them for the peers' acquire.
+// That replaces a system-scope fence in each of the SpMV's ~2 700 CTAs (38 of 104 us per SpMV on two GPUs at 2 M nodes).
+__global__ void dist_flag_kernel(const unsigned long long *__restrict__ peers, int me, int R, uint32_t seq) {
+  asm volatile("griddepcontrol.launch_dependents;");               // the next SpMV may start its constant prologue
+  if (threadIdx.x < (unsigned)R && (int)threadIdx.x != me) {
+    unsigned int *flag = reinterpret_cast<unsigned int *>(peers[threadIdx.x]) + me;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
   }
+}
+void dist_raise_flags(eigkl_handle *h, uint32_t seq) {
+  dist_flag_kernel<<<1, 32, 0, h->stream>>>(h->arena.dev_ptrs.p, h->dist.me, h->dist.R, seq);
+  h->launches++;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -852,7 +857,7 @@ void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const d
     D.exp_ids = P.exp_ids.p; D.blk_exp = P.blk_exp.p;
     D.n_pad = P.n_pad; D.me = P.me; D.R = P.R;
     D.wait_seq = dist->wait_seq; D.push_seq = dist->push_seq;
-    D.ticket = h->arena.ticket.p + 1; D.err = h->arena.err.p;
+    D.err = h->arena.err.p;
     static const int diag = getenv("EIGKL_DIST_DIAG") ? atoi(getenv("EIGKL_DIST_DIAG")) : 0;
     D.diag = diag;
     cudaLaunchConfig_t cfg{};
@@ -868,8 +873,9 @@ void spmv_launch_ex(eigkl_handle *h, const double *xg, const double *xl, const d
     const double *vl = L.val.p;
     h->prof.begin(KC_SPMV, h->stream);
     EIGKL_CUDA(cudaLaunchKernelEx(&cfg, spmv_dist_kernel, rp, vl, xg, xl, z, y, info, scale_inv, store_scaled, L.row_lo, ca, cb, cg, D));
-    h->prof.end(h->stream);
     h->launches++;
+    if (dist->push_seq != 0) dist_raise_flags(h, dist->push_seq);
+    h->prof.end(h->stream);
     return;
   }
   if (L.row_hi <= L.row_lo) return;

@@ -20,7 +20,9 @@ solve = len(sys.argv) > 2 and sys.argv[2] == "solve"
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
 wd = tempfile.mkdtemp()
-if name.startswith("synth"):
+if os.path.exists(name):
+    path = name
+elif name.startswith("synth"):
     path = datasets.write_synthetic(os.path.join(wd, name + ".hgr"), float(name[5:]))
 else:
     path = datasets.materialize(wd, circuits=(name,))[name]
