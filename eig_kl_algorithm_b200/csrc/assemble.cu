@@ -568,10 +568,12 @@ void assemble_kl_graph(eigkl_handle *h) {
     EIGKL_CUDA(cudaMemsetAsync(A.fwd_end.p, 0, (size_t)n * sizeof(int32_t), h->stream));
   }
   // the D-value kernel stages a block's 2048 signed weights: leave room for the block's last row
-  const int64_t chunk = std::min<int64_t>(pick_chunk(h, A.nnz, 8), 1792);
-  A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz, chunk));
+  // (blocks are cut by non-zeros PLUS rows: a node without neighbours has an empty row, and a run of those must not
+  // overflow the kernel's 2048 staged row offsets)
+  const int64_t chunk = std::min<int64_t>(pick_chunk(h, A.nnz + n, 8), 1792);
+  A.n_blocks = (int32_t)std::max<int64_t>(1, ceil_div(A.nnz + n, chunk));
   A.blk_row.alloc((size_t)A.n_blocks + 1);
-  row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, 0, n, chunk, A.n_blocks, A.blk_row.p);
+  row_blocks_kernel<<<grid_for(A.n_blocks + 1), TPB, 0, h->stream>>>(A.rowptr.p, 0, n, chunk, A.n_blocks, A.blk_row.p, 1);
   h->launches++;
   EIGKL_CUDA(cudaGetLastError());
   A.valid = true;

@@ -682,7 +682,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_kernel(const KlLoo
         if (cr == 0) {
           p.t_cut[it_local] = cut; p.t_gain[it_local] = gain; p.t_n1[it_local] = a; p.t_n2[it_local] = b;
           __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));        // swip, cKL.cpp:274-286
-          __stcg(p.state + b, (uint8_t)(ST_LOCK));
+          p.state[b] = (uint8_t)(ST_LOCK);
         }
         if (gain <= 0.0f) { if (++sh_term > p.term_limit) sh_done = 1; }   // cKL.cpp:382-386
         else sh_term = 0;
@@ -1123,6 +1123,9 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
 //     shared-memory words instead of a 256-entry rescan behind the barrier.
 //   * the same two warps then refold the groups of those tiles; when no late rescan was requested (9 swaps in
 //     10) that is the whole epilogue: one barrier instead of three.
+// The D-values and state bytes are read and written with plain loads and stores here: one CTA, ordered by its own
+// barriers, needs no L1 bypass (the .cg forms of the cluster kernel compile to STRONG.GPU accesses, and a strong byte
+// load in the middle of the item phase cost ~2 400 cycles per swap when the state bytes live in global memory).
 // Hub swaps (more neighbours than row threads, or more entries than the staging buffer) take the warp-per-row
 // replay.  The arithmetic is untouched: traces stay byte-identical (test_kl_loop_variants_byte_exact).
 // ---------------------------------------------------------------------------------------------------
@@ -1298,9 +1301,9 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
 #pragma unroll
       for (int r = 0; r < KL_TILE / 32; ++r) {
         const int32_t u = et * KL_TILE + r * 32 + lane;
-        ev[r] = u < p.n ? __ldcg(p.val + u) : 0.0f;
+        ev[r] = u < p.n ? p.val[u] : 0.0f;
         eid[r] = ASC ? (uint32_t)u : (u < p.n ? __ldg(p.rank + u) : 0u);
-        esg[r] = (GBITS && u < p.n) ? ((unsigned)__ldcg(p.state + u) & 3u) : ST_LOCK;
+        esg[r] = (GBITS && u < p.n) ? (unsigned)p.state[u] : ST_LOCK;       // masked where it is used
       }
     }
     const int32_t alo = __ldg(p.rowptr + a), ahi = __ldg(p.rowptr + a + 1);
@@ -1331,7 +1334,7 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
         if (gain <= 0.0f) { if (++S.term > p.term_limit) S.done = 1; }                       // cKL.cpp:382-386
         else S.term = 0;
       } else if (lane == 1) {
-        __stcg(p.state + a, (uint8_t)(ST_SIDE | ST_LOCK));                                   // swip, cKL.cpp:274-286
+        p.state[a] = (uint8_t)(ST_SIDE | ST_LOCK);                                           // swip, cKL.cpp:274-286
         if (!GBITS) bits[a >> 4] = (bits[a >> 4] & ~(3u << ((a & 15) * 2))) | ((ST_SIDE | ST_LOCK) << ((a & 15) * 2));
         if (--S.rem0 == 0) S.done = 1;
       } else if (lane == 2) {
@@ -1357,7 +1360,7 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
           const int32_t u = et * KL_TILE + idx;
           if (u >= p.n || u == a || u == b) continue;
           if ((S.excl[par][es][r] >> lane) & 1u) continue;          // recomputed in this swap: arrives through pkey
-          const unsigned st = GBITS ? esg[r] : bits_get(bits, u);
+          const unsigned st = GBITS ? (esg[r] & 3u) : bits_get(bits, u);
           if (st & ST_LOCK) continue;
           const unsigned long long key = kl_key<ASC>(ev[r], st & ST_SIDE, eid[r]);
           if (st & ST_SIDE) base1 = key > base1 ? key : base1; else base0 = key > base0 ? key : base0;
@@ -1378,7 +1381,7 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
         my_lo = ext.x; my_len = ext.y - ext.x;
         if (CLOCKS && my_len >= 0) KLF_FINE(11);
         my_id = ASC ? (uint32_t)my_v : __ldg(p.rank + my_v);
-        if (GBITS) my_st = (unsigned)__ldcg(p.state + my_v) & 3u;     // needed at the publish: in flight across the entry phase
+        if (GBITS) my_st = (unsigned)p.state[my_v];                   // needed (and masked) at the publish: in flight across the entry phase
         const int32_t tv = my_v / KL_TILE;
         if (tv == ta) atomicOr(&S.excl[par][0][(my_v % KL_TILE) >> 5], 1u << (my_v & 31));
         else if (tv == tb) atomicOr(&S.excl[par][1][(my_v % KL_TILE) >> 5], 1u << (my_v & 31));
@@ -1458,7 +1461,7 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
               if (c4[jj] >= 0) {
                 if (c4[jj] == a) s4[jj] = 1u;                          // the pair being swapped: sides after the swap
                 else if (c4[jj] == b) s4[jj] = 0u;
-                else s4[jj] = GBITS ? ((unsigned)__ldcg(p.state + c4[jj]) & ST_SIDE) : (bits_get(bits, c4[jj]) & ST_SIDE);
+                else s4[jj] = GBITS ? ((unsigned)p.state[c4[jj]] & ST_SIDE) : (bits_get(bits, c4[jj]) & ST_SIDE);
               }
             }
 #pragma unroll
@@ -1477,7 +1480,7 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
         uint32_t khi = 0u, klo = 0u;
         unsigned long long *kp = nullptr, *gp = nullptr;
         if (tid < items) {
-          if (!GBITS) my_st = bits_get(bits, my_v);
+          my_st = GBITS ? (my_st & 3u) : bits_get(bits, my_v);
           float E = 0.0f, I = 0.0f;
           const float *src = stg + my_base + (inc - my_len);
           // batches of 8, the next batch's loads in flight while this one is added; a batch is padded with +0.0f, which
@@ -1499,7 +1502,7 @@ __global__ void __launch_bounds__(KLF_THREADS, 1) kl_loop_flat_kernel(const KlLo
           }
           const float nv = __fsub_rn(E, I);
           if (CLOCKS && nv != 1e30f) KLF_FINE(15);
-          __stcg(p.val + my_v, nv);
+          p.val[my_v] = nv;
           if (!((my_st & ST_LOCK) || my_v == a || my_v == b)) {
             const unsigned sd = my_st & ST_SIDE;
             khi = float_orderable(sd ? -nv : nv);
@@ -1763,8 +1766,9 @@ void kl_run(eigkl_handle *h) {
     auto warm = [&](const void *ptr, size_t bytes) {
       kl_warm_kernel<<<592, 256, 0, st>>>(reinterpret_cast<const uint4 *>(ptr), bytes / 16, reinterpret_cast<unsigned *>(k.ctrl.p + 3));
     };
-    warm(A.nb.p, (size_t)2 * A.nnz * 4); warm(A.col.p, (size_t)A.nnz * 4); warm(A.w.p, (size_t)A.nnz * 4);
-    warm(A.rowptr.p, (size_t)n * 4); warm(k.val.p, (size_t)n * 4);
+    if (atoi(getenv("EIGKL_KL_WARM")) > 1) warm(A.nb.p, (size_t)2 * A.nnz * 4);
+    warm(A.col.p, (size_t)A.nnz * 4); warm(A.w.p, (size_t)A.nnz * 4);
+    warm(A.rowptr.p, (size_t)n * 4); warm(k.val.p, (size_t)n * 4); warm(k.state.p, (size_t)n);
   }
   h->timer.start(st);
   if (local) {

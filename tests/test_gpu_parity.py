@@ -225,6 +225,35 @@ def test_ragged_random_hypergraphs(seed, n_nodes, n_nets, big, oracle, tmp_path)
         assert np.array_equal(tr["gain"].view(np.uint32), ro["gain"].view(np.uint32))
 
 
+def test_long_run_of_isolated_nodes(oracle, tmp_path):
+    """Thousands of consecutive nodes without a pin: their rows are empty, and a row block of the D-value kernel must not
+    collect more of them than it can stage row offsets for (blocks are cut by non-zeros plus rows)."""
+    rng = np.random.default_rng(11)
+    n_nodes = 12000
+    live = np.concatenate([np.arange(0, 1500), np.arange(9000, 12000)])      # nodes 1500..8999 never appear
+    nets = [rng.choice(live, size=int(rng.choice([2, 2, 3, 4])), replace=False) for _ in range(6000)]
+    off = np.zeros(len(nets) + 1, np.int64)
+    off[1:] = np.cumsum([len(x) for x in nets])
+    pins = np.concatenate(nets).astype(np.int32)
+    path = str(tmp_path / "iso.hgr")
+    with open(path, "w") as f:
+        f.write(f"{len(nets)} {n_nodes}\n")
+        for x in nets:
+            f.write(" ".join(str(int(q) + 1) for q in x) + "\n")
+    oh = oracle.OracleHgr(path)
+    o = oracle.OracleKL(oh)
+    side = rng.integers(0, 2, n_nodes).astype(np.uint8)
+    with api.Handle() as h:
+        h.set_pins(n_nodes, off, pins)
+        h.assemble_kl_graph()
+        h.set_partition(side)
+        assert np.array_equal(h.dvalues().view(np.uint32), o.dvalues(side).view(np.uint32))
+        tr = h.kl_run()
+    ro = o.run(side)
+    assert tr["swaps"] == ro["swaps"] and np.array_equal(tr["node1"], ro["node1"]) and np.array_equal(tr["node2"], ro["node2"])
+    assert np.array_equal(tr["cut"].view(np.uint32), ro["cut"].view(np.uint32))
+
+
 def test_bad_inputs_are_rejected(tmp_path):
     with api.Handle() as h:
         off = np.array([0, 3], np.int64)
