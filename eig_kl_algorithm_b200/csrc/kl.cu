@@ -1100,7 +1100,7 @@ __global__ void __launch_bounds__(KL_LOOP_THREADS, 1) kl_loop_local_kernel(const
 
 // ---------------------------------------------------------------------------------------------------
 // The swap loop, third form ("flat"): the same state in shared memory as kl_loop_local_kernel, laid out by ENTRY.
-// ncu on the earlier forms (profiles/r02_kl_flat_ibm10.md): the loop is not waiting for memory -- an L2 hit is 282
+// ncu on the earlier forms (profiles/r02/kl_flat_v1_ncu_lines.txt): the loop is not waiting for memory -- an L2 hit is 282
 // cycles from a lone CTA (tools/micro/chase.cu) and the four dependent trips of a swap explain ~1 100 of its
 // ~10 000 cycles -- it is issue- and barrier-bound: 14 800 warp instructions per swap, a third of them the per-warp
 // slot bookkeeping that spread ~40 neighbour rows over 15 warps, and a third of all warp cycles spent waiting at

@@ -95,7 +95,7 @@ typedef struct {
   int32_t  gs_cache_cols;        /* basis columns the fused kernel keeps in shared memory            */
   int32_t  kl_local;             /* swap loop as one CTA: 1 = tile keys and side bits in shared memory, 2 = tile keys
                                   * in shared memory and state bytes in global memory; 0 = global-memory cluster kernel */
-  int32_t  kl_flat;              /* 1 = the flat form of the shared-memory swap loop (a lane per neighbour row), 0 = warp per row */
+  int32_t  kl_flat;              /* 1 = the flat (by-entry) form of the shared-memory swap loop, 0 = warp per row */
   /* multi-rank Lanczos (nranks > 1): 1 = every rank solved the whole problem (the matrix fits one chip), R = rows
    * partitioned over R ranks; then this rank's rows, the halo values it receives and the rows it pushes per SpMV */
   int32_t  dist_ranks, dist_rows;
