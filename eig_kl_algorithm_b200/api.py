@@ -14,7 +14,6 @@ LIB_PATH = os.path.join(PKG, "lib", "libeigkl.so")
 BIN_DIR = os.path.join(PKG, "bin")
 
 EIGKL_F_PROFILE = 0x1
-EIGKL_F_NO_GRAPH = 0x2
 EIGKL_F_PLAIN_LANCZOS = 0x4
 EIGKL_F_NATURAL_ORDER = 0x8
 

@@ -55,8 +55,7 @@ typedef struct {
   uint32_t flags;            /* EIGKL_F_*                                                         */
 } eigkl_opts;
 
-#define EIGKL_F_PROFILE   0x1u  /* bracket every kernel class with CUDA events (see eigkl_stats)  */
-#define EIGKL_F_NO_GRAPH  0x2u  /* reserved                                                          */
+#define EIGKL_F_PROFILE   0x1u  /* bracket every kernel class with CUDA events (see eigkl_stats); bit 0x2 is unused */
 #define EIGKL_F_NATURAL_ORDER 0x8u /* EIG stage keeps the file's node numbering (default: nodes renumbered by first net, for gather locality) */
 #define EIGKL_F_PLAIN_LANCZOS 0x4u /* no Chebyshev filter: Lanczos on L itself (degree-1 map), as Spectra does */
 
