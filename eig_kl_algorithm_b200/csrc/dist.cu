@@ -219,9 +219,7 @@ static bool peer_arena_ensure(eigkl_handle *h, size_t vec_bytes) {
   unsigned long long tbl[EIGKL_MAX_RANKS] = {0};
   for (int q = 0; q < R; ++q) tbl[q] = (unsigned long long)(uintptr_t)a.peer[q];
   EIGKL_CUDA(cudaMemcpyAsync(a.dev_ptrs.p, tbl, sizeof(tbl), cudaMemcpyHostToDevice, st));
-  a.ticket.alloc(8);
   a.err.alloc(4);
-  EIGKL_CUDA(cudaMemsetAsync(a.ticket.p, 0, 8 * sizeof(unsigned int), st));
   EIGKL_CUDA(cudaMemsetAsync(a.err.p, 0, 4 * sizeof(int), st));
   EIGKL_CUDA(cudaStreamSynchronize(st));
   return true;

@@ -222,8 +222,7 @@ struct PeerArena {
   size_t vec_bytes = 0;          // bytes of one vector buffer in the current layout
   void *peer[EIGKL_MAX_RANKS] = {nullptr};   // peer[q]: rank q's arena in this process' address space
   DBuf<unsigned long long> dev_ptrs;         // the same table on the device
-  DBuf<unsigned int> ticket;     // last-CTA tickets of the push kernels
-  DBuf<int> err;                 // [0] != 0: a flag wait timed out
+  DBuf<int> err;                 // [0] != 0: a flag wait (1) or an all-reduce wait (2) timed out
   uint32_t seq = 0;              // halo productions issued so far (identical on every rank)
   uint32_t red_seq = 0;          // one-shot all-reduces issued so far (identical on every rank)
   int state = 0;                 // 0 untried, 1 usable, -1 peer mapping unavailable (every rank then solves replicated)

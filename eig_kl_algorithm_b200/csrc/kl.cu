@@ -22,6 +22,10 @@
 //          sum replayed through warp shuffles)
 //      S4  tiles that contain a touched node are rescanned (first warp to stamp the tile does it)
 //    Nothing returns to the host until the pass ends; the trace is buffered in HBM.
+//    Three forms of that loop, byte-identical in their traces: kl_loop_kernel (state in global memory, 1..16-CTA cluster:
+//    graphs beyond 2 M nodes, or kl_cluster asked for), kl_loop_local_kernel (one CTA, keys and side bits in shared
+//    memory, a warp per neighbour row) and kl_loop_flat_kernel (the default up to 2 M nodes: the same shared-memory state,
+//    the neighbour rows laid out as one flat list of entries; see the comment above it).
 //  * Initial cut (kl_cut0): the reference's one-thread evaluation order, including the iteration order
 //    of its unordered_set of right nodes, rebuilt with sorts (stl_order.h explains the rule).
 #include "internal.h"
@@ -1667,15 +1671,6 @@ __global__ void kl_undo_kernel(const int32_t *__restrict__ n1, const int32_t *__
   state[n1[i]] = (uint8_t)ST_LOCK;                   // back on side 0 (still marked: the pass is over)
   state[n2[i]] = (uint8_t)(ST_SIDE | ST_LOCK);       // back on side 1
 }
-// reads the swap loop's arrays once so that its dependent loads find them in L2 (tuning experiment, EIGKL_KL_WARM)
-__global__ void kl_warm_kernel(const uint4 *__restrict__ p, size_t n16, unsigned *__restrict__ sink) {
-  unsigned s = 0;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
-    const uint4 v = __ldcg(p + i);
-    s += v.x ^ v.y ^ v.z ^ v.w;
-  }
-  if (s == 0x9E3779B9u) *sink = s;
-}
 int64_t kl_rollback(eigkl_handle *h, float *best_cut) {
   auto &k = h->kl;
   EIGKL_REQUIRE(k.have_partition && k.consumed, EIGKL_E_ARG, "eigkl_kl_rollback: no finished KL pass to roll back");
@@ -1773,14 +1768,6 @@ void kl_run(eigkl_handle *h) {
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = (unsigned)nc; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  if (local && getenv("EIGKL_KL_WARM")) {
-    auto warm = [&](const void *ptr, size_t bytes) {
-      kl_warm_kernel<<<592, 256, 0, st>>>(reinterpret_cast<const uint4 *>(ptr), bytes / 16, reinterpret_cast<unsigned *>(k.ctrl.p + 3));
-    };
-    if (atoi(getenv("EIGKL_KL_WARM")) > 1) warm(A.nb.p, (size_t)2 * A.nnz * 4);
-    warm(A.col.p, (size_t)A.nnz * 4); warm(A.w.p, (size_t)A.nnz * 4);
-    warm(A.rowptr.p, (size_t)n * 4); warm(k.val.p, (size_t)n * 4); warm(k.state.p, (size_t)n);
-  }
   h->timer.start(st);
   if (local) {
     KlLocalParams q;
