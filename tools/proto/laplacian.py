@@ -1,6 +1,18 @@
-import sys, gzip, numpy as np, scipy.sparse as sp, scipy.sparse.linalg as sla, time
+"""The clique-model Laplacian (cEIG.cpp:86-133: weight 2/k per pin pair of a k-pin net) of a shipped circuit, scipy CSR."""
+import gzip
+import os
+import sys
+import time
+
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as sla
+
+DATA = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), 'tests', 'data', 'circuit')
+
+
 def load_L(name):
-    f=gzip.open(f'' + __import__('os').path.join(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.dirname(__import__('os').path.abspath(__file__)))), 'tests', 'data', 'circuit', '') + f'{name}.hgr.gz','rt').read().split('\n')
+    f = gzip.open(os.path.join(DATA, name + '.hgr.gz'), 'rt').read().split('\n')
     nn,N=map(int,f[0].split()[:2])
     r=[];c=[];v=[]
     for line in f[1:1+nn]:
