@@ -685,6 +685,13 @@ def main():
                 "gpu_launches": m["gpu_launches"], "roofline": m["roofline"], "kernels": m["kernels"], "cpu_baseline": m["cpu_baseline"]}
         if world > 1:
             line["parity"] = m["parity"]
+            if m["config"].get("dist_ranks", 1) <= 1:
+                # the matrix fits one chip: every rank ran the complete bipartition inside the timed region (same input, same
+                # result).  `value` counts that as ONE bipartition (strong scaling of one problem: flat by construction); what the N
+                # GPUs completed in that time is N bipartitions -- the throughput when each rank is given a circuit of its own
+                line["replicas"] = {"bipartitions_completed_per_step": world, "aggregate_passes_per_s": world * m["value"],
+                                    "note": "replicas only (SURVEY.md 8e): no data-path collective; the ranks do not share work on a problem "
+                                            "that one chip solves in ~24 ms"}
         if extras:
             line["workloads"] = {k: {kk: vv for kk, vv in v.items() if kk not in ("workload", "unit", "clocks")} for k, v in extras.items()}
         line.update(legs)
