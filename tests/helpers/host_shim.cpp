@@ -60,6 +60,9 @@ int shim_tridiag_top(int n, const double *d, const double *e, int k, double *the
   try { tridiag_top_eig(n, d, e, k, theta, Y); return 0; } catch (const Error &e2) { return e2.code; }
 }
 // product's order replay (stl_order.h), host instantiation
+int shim_write_partition(const char *path, const uint8_t *side, int32_t n) {
+  try { write_partition_file(path, side, n); return 0; } catch (const Error &e) { return e.code; }
+}
 void shim_stl_order(const uint32_t *keys, int32_t n, int32_t *order) {
   std::vector<int32_t> next((size_t)std::max(n, 1)), bkt(stl_final_buckets((uint32_t)n));
   int32_t head;

@@ -205,6 +205,26 @@ def test_tridiag_top_eig(shim, n):
     assert np.abs(Y.T @ Y - np.eye(k)).max() < 1e-10
 
 
+def test_partition_writer_format_and_thread_independence(shim, tmp_path, monkeypatch):
+    """`--partition-out` file: one `node<TAB>side` row per node, ascending, whatever the writer's thread count."""
+    rng = np.random.default_rng(5)
+    n = 100003
+    side = rng.integers(0, 2, n).astype(np.uint8)
+    side[7] = 3                                   # only bit 0 is the side (bit 1 is the lock mark of a finished pass)
+    shim.shim_write_partition.argtypes = [C.c_char_p, C.POINTER(C.c_uint8), C.c_int32]
+    outs = []
+    for threads in ("1", "7"):
+        monkeypatch.setenv("EIGKL_IO_THREADS", threads)
+        out = str(tmp_path / f"part_{threads}.txt")
+        assert shim.shim_write_partition(out.encode(), _p(side, C.c_uint8), n) == 0
+        outs.append(open(out, "rb").read())
+    assert outs[0] == outs[1]
+    rows = outs[0].decode().split("\n")
+    assert rows[-1] == "" and len(rows) == n + 1
+    assert rows[0] == f"0\t{side[0] & 1}" and rows[7] == "7\t1" and rows[n - 1] == f"{n - 1}\t{side[n - 1] & 1}"
+    assert shim.shim_write_partition(str(tmp_path / "no_such_dir" / "x.txt").encode(), _p(side, C.c_uint8), n) != 0
+
+
 def test_trace_writer_format(eigkl_lib, tmp_path):
     # cKL.cpp:315,380 -- default ostream float formatting (6 significant digits)
     cut = np.array([27.75, 26.875, 36.958332, 1153.3374, 740.9452], np.float32)
